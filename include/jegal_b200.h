@@ -1,0 +1,166 @@
+/*
+ * jegal_b200 — C ABI of the B200-native (sm_100a) JEGAL cross-modal scoring path.
+ *
+ * The reference (Sindhu-Hegde/jegal) has no FFI: its scoring "API" is a set of
+ * module-level Python functions that call torch-CPU / numpy.  Each entry point
+ * below names the reference code it replaces (paths relative to the reference
+ * root).  The Python mirror of those functions (same names, same arguments)
+ * lives in jegal_b200/scoring.py and binds this header through ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - return 0 on success, a negative jegal_status otherwise; no C++ exception
+ *     crosses the boundary; jegal_last_error(ctx) describes the last failure.
+ *   - every "dev" pointer is caller-owned device memory on the ctx's device,
+ *     16-byte aligned and contiguous; "host" pointers are ordinary host memory
+ *     that is consumed before the call returns.
+ *   - all kernels are enqueued on `stream` (a cudaStream_t passed as void*) and
+ *     the call returns without synchronising.  The *_host convenience entry
+ *     points (suffix _host) are the exception: they copy in, run, copy out and
+ *     synchronise, because that is what a drop-in of a CPU function must do.
+ *   - a ctx is bound to one device and is not thread-safe.
+ *   - there is no CPU fallback: a device that is not sm_100 yields
+ *     JEGAL_ERR_DEVICE.
+ *   - D (embedding width) is fixed at 512 (models/jegal.py:18,71-76).
+ */
+#ifndef JEGAL_B200_H_
+#define JEGAL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JEGAL_EMB_DIM 512
+
+typedef enum {
+  JEGAL_OK = 0,
+  JEGAL_ERR_ARG = -1,         /* bad argument (null pointer, negative size, bad enum) */
+  JEGAL_ERR_DEVICE = -2,      /* not an sm_100 device / device mismatch */
+  JEGAL_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed */
+  JEGAL_ERR_UNSUPPORTED = -4, /* shape outside what the kernels cover (see message) */
+  JEGAL_ERR_NOMEM = -5
+} jegal_status;
+
+typedef enum { JEGAL_F32 = 0, JEGAL_F16 = 1, JEGAL_BF16 = 2 } jegal_dtype;
+
+/* How the T x W cosine tile of one (gesture clip, content clip) pair is pooled.
+ * MEAN_MEAN with the per-clip scales returned by jegal_prep(.., inv_meannorm)
+ * reproduces evaluation/evaluate_retrieval.py:30-31,38-48 and
+ * evaluation/evaluate_asd.py:31-36,43-47 exactly. */
+typedef enum {
+  JEGAL_POOL_MEAN_MEAN = 0,    /* mean over frames and words            */
+  JEGAL_POOL_MAX_T_MEAN_W = 1, /* max over frames, then mean over words */
+  JEGAL_POOL_MAX_W_MEAN_T = 2, /* max over words, then mean over frames */
+  JEGAL_POOL_MAX_MAX = 3       /* max over both                         */
+} jegal_pool_mode;
+
+typedef struct jegal_ctx jegal_ctx;
+/* Ragged layout of one packed operand: n_clips clips, clip i owns rows
+ * [cu_len[i], cu_len[i+1]) of a [cu_len[n_clips], 512] row-major matrix. */
+typedef struct jegal_layout jegal_layout;
+
+const char* jegal_version(void);
+
+int jegal_ctx_create(int device, jegal_ctx** out);
+void jegal_ctx_destroy(jegal_ctx* ctx);
+const char* jegal_last_error(const jegal_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int64_t jegal_launch_count(const jegal_ctx* ctx);
+
+/* cu_len_host: n_clips + 1 non-decreasing int32 offsets starting at 0.
+ * Uploads the offsets and builds the row->clip map on the device (async on stream). */
+int jegal_layout_create(jegal_ctx* ctx, const int32_t* cu_len_host, int32_t n_clips, void* stream,
+                        jegal_layout** out);
+void jegal_layout_destroy(jegal_layout* layout);
+int64_t jegal_layout_rows(const jegal_layout* layout);
+int32_t jegal_layout_clips(const jegal_layout* layout);
+
+/* K0 — normalise + cast (+ per-clip mean-vector norm), one pass over the rows.
+ * Replaces F.normalize(x, p=2, dim=-1) at inference_embs.py:630-636,
+ * evaluation/evaluate_spotting.py:49-50 and the numpy .mean(axis=0) +
+ * F.normalize / CosineSimilarity norms at evaluate_retrieval.py:30-31,41,44 and
+ * evaluate_asd.py:32,36,45-47.
+ *   emb_dev        [rows, 512] in `in_dtype`
+ *   normalize_rows 1: out row = row / max(||row||, row_eps) (fp32 math), 0: cast only
+ *   out_rows_dev   [rows, 512] in `out_dtype` (JEGAL_BF16 or JEGAL_F16)
+ *   inv_meannorm_dev (nullable) [n_clips] fp32: 1 / max(||mean of the clip's INPUT rows||, mean_eps)
+ */
+int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype,
+               int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
+               float* inv_meannorm_dev, void* stream);
+
+/* K1 — all-pairs fused similarity + pooling (tcgen05 / TMEM / TMA).
+ * scores[g * ld_g + c * ld_c] = gscale[g] * cscale[c] * pool_{t,w}(G_g C_c^T).
+ * Generalises get_similarity_matrix (evaluation/evaluate_retrieval.py:38-48) from
+ * mean-pooled vectors to the frame x word tile of every clip pair; the T x W
+ * similarity tile lives only in tensor memory.
+ *   gest_rows_dev / cont_rows_dev : outputs of jegal_prep, both in `op_dtype`
+ *   gscale_dev / cscale_dev       : nullable per-clip fp32 multipliers (> 0)
+ *   (ld_g, ld_c) must be (n_cont, 1) or (1, n_gest): a dense matrix or its transpose.
+ */
+int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout,
+                           const void* gest_rows_dev, const jegal_layout* cont_layout,
+                           const void* cont_rows_dev, int op_dtype, int pool_mode,
+                           const float* gscale_dev, const float* cscale_dev, float* scores_dev,
+                           int64_t ld_g, int64_t ld_c, void* stream);
+
+/* K2 — per-query top-k of a dense [n_q, n_g] fp32 score matrix (row stride ld).
+ * Descending by score, ties broken towards the lower index; indices are
+ * returned + idx_offset (the shard's first global clip).  1 <= k <= 32.
+ * Replaces the full np.sort in compute_metrics (evaluate_retrieval.py:52). */
+int jegal_topk(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g, int64_t ld,
+               int32_t k, int32_t idx_offset, float* topk_val_dev, int32_t* topk_idx_dev,
+               void* stream);
+
+/* Merge n_lists sorted top-k lists per query ([n_lists, n_q, k] val/idx, e.g. the
+ * all-gathered per-shard results) into one [n_q, k] list with the same ordering
+ * rule as jegal_topk. */
+int jegal_topk_merge(jegal_ctx* ctx, const float* vals_dev, const int32_t* idxs_dev,
+                     int32_t n_lists, int32_t n_q, int32_t k, float* out_val_dev,
+                     int32_t* out_idx_dev, void* stream);
+
+/* Rank of the ground-truth column of every row of a dense [n_q, n_g] matrix:
+ * gt_dev[i] (nullable => i, the diagonal) is the positive's column.
+ *   n_greater[i] = #{j : x[i,j] >  x[i,gt]}   (the reference's `ind`, evaluate_retrieval.py:52-57)
+ *   n_equal[i]   = #{j : x[i,j] == x[i,gt]}   (>= 1; the reference over-counts rows with ties)
+ * Replaces np.sort + np.where in compute_metrics (evaluate_retrieval.py:51-65). */
+int jegal_rank_of_positive(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g,
+                           int64_t ld_row, int64_t ld_col, const int32_t* gt_dev,
+                           int32_t* n_greater_dev, int32_t* n_equal_dev, void* stream);
+
+/* K3 — word spotting (evaluation/evaluate_spotting.py:39-90, utils/plot_heatmap.py:34-59).
+ * For clip i: A = softmax_w((G_i C_i^T) / tau) (softmax over words per frame).
+ *   word_idx_dev[i]   the target word's row of A^T
+ *   heat_dev          (nullable) [rows of gest_layout] fp32: A[:, word_idx] for every frame
+ *   full_heat_dev     (nullable) [sum_i T_i * W_i] fp32: the whole (W_i x T_i) matrix of clip i,
+ *                     word-major as the reference returns it, at offset full_off_dev[i]
+ *   pred_frame_dev[i] argmax_t A[t, word_idx] (first maximum); pred_score_dev[i] its value
+ *   correct_dev[i]    (nullable; needs win_lo/win_hi) 1 iff win_lo[i] <= pred <= win_hi[i] and
+ *                     pred_score >= thresh  (evaluate_spotting.py:75-82)
+ */
+int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
+               const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
+               const int32_t* word_idx_dev, float tau, float* heat_dev, float* full_heat_dev,
+               const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
+               const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh,
+               uint8_t* correct_dev, void* stream);
+
+/* K4 — grouped scoring (evaluation/evaluate_asd.py:43-51,94-100): n_pairs listed
+ * (gesture clip, content clip) pairs in groups of `group_size` consecutive pairs.
+ *   scores_dev[p]  pooled score of pair p (x gscale x cscale as in K1)
+ *   probs_dev      (nullable) softmax(scores / tau) within each group
+ *   argmax_dev     (nullable) [n_pairs / group_size] first index of the group maximum
+ */
+int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
+                        const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
+                        int pool_mode, const float* gscale_dev, const float* cscale_dev,
+                        const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
+                        int32_t group_size, float tau, float* scores_dev, float* probs_dev,
+                        int32_t* argmax_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JEGAL_B200_H_ */

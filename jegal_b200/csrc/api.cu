@@ -1,0 +1,338 @@
+// C ABI (include/jegal_b200.h): context, ragged layouts, tile planning and the
+// host side of every entry point.  No torch types, no exceptions across the ABI.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace jegal {
+
+int set_err(jegal_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows,
+                      int op_dtype) {
+  auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ctx->encode_tiled);
+  const CUtensorMapDataType dt =
+      op_dtype == JEGAL_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kD), static_cast<cuuint64_t>(n_rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kD) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kTileRows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, dt, 2, const_cast<void*>(rows_dev), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_err(ctx, JEGAL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return JEGAL_OK;
+}
+
+namespace {
+
+// Pack whole clips greedily into column tiles of `width` rows.  A clip longer
+// than `width` is cut into pieces (flagged partial) when the pooling allows it.
+int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_split,
+                 jegal_layout::CTileSet* set) {
+  set->width = width;
+  set->allow_split = allow_split;
+  set->any_partial = false;
+  set->host.clear();
+  const std::vector<int32_t>& cu = L->cu_host;
+  int32_t i = 0;
+  while (i < L->n_clips) {
+    const int32_t len = cu[i + 1] - cu[i];
+    if (len > width) {
+      if (!allow_split)
+        return set_err(ctx, JEGAL_ERR_UNSUPPORTED,
+                       "clip " + std::to_string(i) + " has " + std::to_string(len) +
+                           " rows on the column side; a max-then-mean pooling needs <= " +
+                           std::to_string(width));
+      for (int32_t off = 0; off < len; off += width) {
+        CTile t{};
+        t.row0 = cu[i] + off;
+        t.n_valid = std::min(width, len - off);
+        t.clip0 = i;
+        t.partial = 1;
+        const int32_t e = t.n_valid - 1;
+        t.endmask[e >> 5] |= 1u << (e & 31);
+        set->host.push_back(t);
+        set->any_partial = true;
+      }
+      ++i;
+      continue;
+    }
+    CTile t{};
+    t.row0 = cu[i];
+    t.clip0 = i;
+    int32_t used = 0;
+    while (i < L->n_clips) {
+      const int32_t l = cu[i + 1] - cu[i];
+      if (used + l > width) break;
+      used += l;
+      const int32_t e = used - 1;
+      t.endmask[e >> 5] |= 1u << (e & 31);
+      ++i;
+    }
+    t.n_valid = used;
+    set->host.push_back(t);
+  }
+  set->n = static_cast<int>(set->host.size());
+  return JEGAL_OK;
+}
+
+int get_ctiles(jegal_ctx* ctx, jegal_layout* L, int width, bool allow_split, cudaStream_t stream,
+               jegal_layout::CTileSet** out) {
+  for (auto* s : L->ctile_sets) {
+    // a no-split set without partial tiles also serves callers that would allow splitting
+    if (s->width == width && (s->allow_split == allow_split || !s->any_partial)) {
+      *out = s;
+      return JEGAL_OK;
+    }
+  }
+  auto* set = new (std::nothrow) jegal_layout::CTileSet();
+  if (!set) return set_err(ctx, JEGAL_ERR_NOMEM, "out of host memory");
+  int rc = build_ctiles(ctx, L, width, allow_split, set);
+  if (rc != JEGAL_OK) {
+    delete set;
+    return rc;
+  }
+  if (set->n > 0) {
+    cudaError_t e = cudaMalloc(&set->dev, sizeof(CTile) * set->n);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(set->dev, set->host.data(), sizeof(CTile) * set->n, cudaMemcpyHostToDevice, stream);
+    // one-time cost: later calls may run on another stream
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+      if (set->dev) cudaFree(set->dev);
+      delete set;
+      return set_err(ctx, JEGAL_ERR_CUDA, std::string("ctile upload: ") + cudaGetErrorString(e));
+    }
+  }
+  L->ctile_sets.push_back(set);
+  *out = set;
+  return JEGAL_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+}  // namespace jegal
+
+using namespace jegal;
+
+extern "C" {
+
+const char* jegal_version(void) { return "jegal_b200 0.1 (sm_100a)"; }
+
+int jegal_ctx_create(int device, jegal_ctx** out) {
+  if (!out) return JEGAL_ERR_ARG;
+  *out = nullptr;
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JEGAL_ERR_DEVICE;
+  if (prop.major != 10) return JEGAL_ERR_DEVICE;  // sm_100a only: no fallback path exists
+  if (cudaSetDevice(device) != cudaSuccess) return JEGAL_ERR_DEVICE;
+  auto* ctx = new (std::nothrow) jegal_ctx();
+  if (!ctx) return JEGAL_ERR_NOMEM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return JEGAL_ERR_CUDA;
+  }
+  ctx->encode_tiled = fn;
+  *out = ctx;
+  return JEGAL_OK;
+}
+
+void jegal_ctx_destroy(jegal_ctx* ctx) { delete ctx; }
+
+const char* jegal_last_error(const jegal_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int64_t jegal_launch_count(const jegal_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int jegal_layout_create(jegal_ctx* ctx, const int32_t* cu_len_host, int32_t n_clips, void* stream_,
+                        jegal_layout** out) {
+  if (!ctx || !out || !cu_len_host || n_clips < 0) return set_err(ctx, JEGAL_ERR_ARG, "layout_create: null/negative argument");
+  *out = nullptr;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (cu_len_host[0] != 0) return set_err(ctx, JEGAL_ERR_ARG, "layout_create: cu_len[0] must be 0");
+  bool aligned = true;
+  int32_t max_len = 0;
+  for (int32_t i = 0; i < n_clips; ++i) {
+    const int32_t b = cu_len_host[i], e = cu_len_host[i + 1];
+    if (e <= b)
+      return set_err(ctx, JEGAL_ERR_ARG, "layout_create: clip " + std::to_string(i) + " is empty or offsets decrease");
+    max_len = std::max(max_len, e - b);
+    if ((b >> 5) != ((e - 1) >> 5)) aligned = false;
+  }
+  auto* L = new (std::nothrow) jegal_layout();
+  if (!L) return set_err(ctx, JEGAL_ERR_NOMEM, "out of host memory");
+  L->ctx = ctx;
+  L->n_clips = n_clips;
+  L->rows = cu_len_host[n_clips];
+  L->max_len = max_len;
+  L->warp_aligned = aligned;
+  L->cu_host.assign(cu_len_host, cu_len_host + n_clips + 1);
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e == cudaSuccess) e = cudaMalloc(&L->cu_dev, sizeof(int32_t) * (n_clips + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&L->row2clip_dev, sizeof(int32_t) * std::max<int64_t>(L->rows, 1));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(L->cu_dev, L->cu_host.data(), sizeof(int32_t) * (n_clips + 1), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) {
+    jegal_layout_destroy(L);
+    return set_err(ctx, JEGAL_ERR_CUDA, std::string("layout_create: ") + cudaGetErrorString(e));
+  }
+  int rc = launch_row2clip(ctx, L->cu_dev, n_clips, L->rows, L->row2clip_dev, stream);
+  if (rc == JEGAL_OK && cudaStreamSynchronize(stream) != cudaSuccess)  // one-time: layout is usable on any stream
+    rc = set_err(ctx, JEGAL_ERR_CUDA, "layout_create: synchronize failed");
+  if (rc != JEGAL_OK) {
+    jegal_layout_destroy(L);
+    return rc;
+  }
+  *out = L;
+  return JEGAL_OK;
+}
+
+void jegal_layout_destroy(jegal_layout* L) {
+  if (!L) return;
+  if (L->cu_dev) cudaFree(L->cu_dev);
+  if (L->row2clip_dev) cudaFree(L->row2clip_dev);
+  for (auto* s : L->ctile_sets) {
+    if (s->dev) cudaFree(s->dev);
+    delete s;
+  }
+  delete L;
+}
+
+int64_t jegal_layout_rows(const jegal_layout* L) { return L ? L->rows : 0; }
+int32_t jegal_layout_clips(const jegal_layout* L) { return L ? L->n_clips : 0; }
+
+int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype,
+               int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
+               float* inv_meannorm_dev, void* stream) {
+  if (!ctx || !layout || !emb_dev || !out_rows_dev) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
+  if ((reinterpret_cast<uintptr_t>(emb_dev) | reinterpret_cast<uintptr_t>(out_rows_dev)) & 15u)
+    return set_err(ctx, JEGAL_ERR_ARG, "prep: buffers must be 16-byte aligned");
+  return launch_prep(ctx, layout, emb_dev, in_dtype, normalize_rows, row_eps, mean_eps, out_dtype,
+                     out_rows_dev, inv_meannorm_dev, static_cast<cudaStream_t>(stream));
+}
+
+int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
+                           const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
+                           int pool_mode, const float* gscale_dev, const float* cscale_dev,
+                           float* scores_dev, int64_t ld_g, int64_t ld_c, void* stream_) {
+  if (!ctx || !gest_layout || !cont_layout || !gest_rows_dev || !cont_rows_dev || !scores_dev)
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: null argument");
+  if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16)
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: op_dtype must be JEGAL_BF16 or JEGAL_F16");
+  const int32_t nG = gest_layout->n_clips, nC = cont_layout->n_clips;
+  if (!((ld_g == nC && ld_c == 1) || (ld_g == 1 && ld_c == nG)))
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: (ld_g, ld_c) must be (n_cont, 1) or (1, n_gest)");
+  if (nG == 0 || nC == 0) return JEGAL_OK;
+  if ((reinterpret_cast<uintptr_t>(gest_rows_dev) | reinterpret_cast<uintptr_t>(cont_rows_dev)) & 15u)
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: operand rows must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+  // Orientation: the first reduction must run along columns (in-thread).
+  bool cols_are_gest;
+  int col_op, row_op;
+  switch (pool_mode) {
+    case JEGAL_POOL_MEAN_MEAN: cols_are_gest = false; col_op = OP_SUM; row_op = OP_SUM; break;
+    case JEGAL_POOL_MAX_T_MEAN_W: cols_are_gest = true; col_op = OP_MAX; row_op = OP_SUM; break;
+    case JEGAL_POOL_MAX_W_MEAN_T: cols_are_gest = false; col_op = OP_MAX; row_op = OP_SUM; break;
+    case JEGAL_POOL_MAX_MAX: cols_are_gest = false; col_op = OP_MAX; row_op = OP_MAX; break;
+    default: return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: bad pool_mode");
+  }
+  const int force = env_int("JEGAL_SIMPOOL_COLS", -1);  // testing knob: 0 = content, 1 = gesture
+  if (force >= 0 && col_op == row_op) cols_are_gest = force != 0;
+
+  jegal_layout* LC = const_cast<jegal_layout*>(cols_are_gest ? gest_layout : cont_layout);
+  const jegal_layout* LR = cols_are_gest ? cont_layout : gest_layout;
+  const void* rowsC = cols_are_gest ? gest_rows_dev : cont_rows_dev;
+  const void* rowsR = cols_are_gest ? cont_rows_dev : gest_rows_dev;
+
+  int cg = env_int("JEGAL_CTA_GROUP", 2);
+  if (cg != 1 && cg != 2) cg = 2;
+  if (ctx->sm_count < 2) cg = 1;
+  const int width = kTileRows * cg;
+
+  jegal_layout::CTileSet* cts = nullptr;
+  int rc = get_ctiles(ctx, LC, width, col_op == row_op, stream, &cts);
+  if (rc != JEGAL_OK) return rc;
+
+  SimpoolParams p{};
+  p.ctiles = cts->dev;
+  p.n_ctiles = cts->n;
+  p.n_rtiles = static_cast<int32_t>((LR->rows + width - 1) / width);
+  const int64_t chunk_bytes = static_cast<int64_t>(env_int("JEGAL_CHUNK_MB", 24)) << 20;
+  p.chunk_rtiles = static_cast<int32_t>(std::max<int64_t>(1, chunk_bytes / (static_cast<int64_t>(width) * kD * 2)));
+  p.n_rows_R = static_cast<int32_t>(LR->rows);
+  p.row2clip_R = LR->row2clip_dev;
+  p.cu_R = LR->cu_dev;
+  p.cu_C = LC->cu_dev;
+  p.rscale = cols_are_gest ? cscale_dev : gscale_dev;
+  p.cscale = cols_are_gest ? gscale_dev : cscale_dev;
+  p.out = scores_dev;
+  p.ld_r = cols_are_gest ? ld_c : ld_g;
+  p.ld_c = cols_are_gest ? ld_g : ld_c;
+  p.idesc = ptx::make_idesc_f16(op_dtype == JEGAL_BF16 ? 1u : 0u, static_cast<uint32_t>(width),
+                                static_cast<uint32_t>(width));
+
+  // Results of clips that straddle warps / row tiles / column tiles are combined
+  // with atomics and need an initialised output.
+  if (!LR->warp_aligned || cts->any_partial) {
+    rc = launch_fill_f32(ctx, scores_dev, static_cast<int64_t>(nG) * nC, row_op == OP_MAX ? -INFINITY : 0.0f, stream);
+    if (rc != JEGAL_OK) return rc;
+  }
+
+  CUtensorMap tmR, tmC;
+  rc = make_operand_tmap(ctx, &tmR, rowsR, LR->rows, op_dtype);
+  if (rc != JEGAL_OK) return rc;
+  rc = make_operand_tmap(ctx, &tmC, rowsC, LC->rows, op_dtype);
+  if (rc != JEGAL_OK) return rc;
+  return launch_simpool(ctx, cg, col_op, row_op, tmR, tmC, p, stream);
+}
+
+int jegal_topk(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
+               int32_t idx_offset, float* topk_val_dev, int32_t* topk_idx_dev, void* stream) {
+  if (!ctx || !scores_dev || !topk_val_dev || !topk_idx_dev) return set_err(ctx, JEGAL_ERR_ARG, "topk: null argument");
+  if (k < 1 || k > 32) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "topk: k must be in [1, 32]");
+  if (n_q < 0 || n_g < 0 || ld < n_g) return set_err(ctx, JEGAL_ERR_ARG, "topk: bad shape");
+  return launch_topk(ctx, scores_dev, n_q, n_g, ld, k, idx_offset, topk_val_dev, topk_idx_dev,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int jegal_topk_merge(jegal_ctx* ctx, const float* vals_dev, const int32_t* idxs_dev, int32_t n_lists,
+                     int32_t n_q, int32_t k, float* out_val_dev, int32_t* out_idx_dev, void* stream) {
+  if (!ctx || !vals_dev || !idxs_dev || !out_val_dev || !out_idx_dev)
+    return set_err(ctx, JEGAL_ERR_ARG, "topk_merge: null argument");
+  if (k < 1 || k > 32) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "topk_merge: k must be in [1, 32]");
+  if (n_lists < 1 || n_q < 0) return set_err(ctx, JEGAL_ERR_ARG, "topk_merge: bad shape");
+  return launch_topk_merge(ctx, vals_dev, idxs_dev, n_lists, n_q, k, out_val_dev, out_idx_dev,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int jegal_rank_of_positive(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g,
+                           int64_t ld_row, int64_t ld_col, const int32_t* gt_dev, int32_t* n_greater_dev,
+                           int32_t* n_equal_dev, void* stream) {
+  if (!ctx || !scores_dev || !n_greater_dev) return set_err(ctx, JEGAL_ERR_ARG, "rank_of_positive: null argument");
+  if (n_q < 0 || n_g < 0) return set_err(ctx, JEGAL_ERR_ARG, "rank_of_positive: bad shape");
+  if (!gt_dev && n_q > n_g) return set_err(ctx, JEGAL_ERR_ARG, "rank_of_positive: diagonal needs n_q <= n_g");
+  return launch_rank_of_positive(ctx, scores_dev, n_q, n_g, ld_row, ld_col, gt_dev, n_greater_dev,
+                                 n_equal_dev, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

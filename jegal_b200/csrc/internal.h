@@ -1,0 +1,110 @@
+// Internal (non-ABI) declarations shared by the .cu translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/jegal_b200.h"
+
+namespace jegal {
+
+constexpr int kD = JEGAL_EMB_DIM;  // 512
+constexpr int kBlockK = 64;        // one 128-byte swizzle atom of 16-bit elements
+constexpr int kNumKBlocks = kD / kBlockK;
+constexpr int kTileRows = 128;     // operand rows per CTA per TMA box
+
+// One column tile of the all-pairs kernel: up to `width` consecutive rows of the
+// column operand holding whole clips (or one piece of an over-long clip).
+struct CTile {
+  int32_t row0;     // first operand row of the tile
+  int32_t n_valid;  // columns that belong to this tile's clips
+  int32_t clip0;    // first clip index
+  int32_t partial;  // 1: the tile holds a piece of a split clip -> results are combined atomically
+  uint32_t endmask[8];  // bit j of word c: column 32c+j is the last column of a segment
+};
+static_assert(sizeof(CTile) == 48, "CTile layout");
+
+struct SimpoolParams {
+  const CTile* ctiles;
+  int32_t n_ctiles;
+  int32_t n_rtiles;      // row tiles of (128 * cta_group) rows
+  int32_t chunk_rtiles;  // row tiles per L2-resident phase
+  int32_t n_rows_R;
+  const int32_t* row2clip_R;
+  const int32_t* cu_R;
+  const int32_t* cu_C;
+  const float* rscale;  // nullable
+  const float* cscale;  // nullable
+  float* out;
+  int64_t ld_r;
+  int64_t ld_c;
+  uint32_t idesc;
+};
+
+enum Op : int { OP_SUM = 0, OP_MAX = 1 };
+
+}  // namespace jegal
+
+struct jegal_ctx {
+  int device = -1;
+  int sm_count = 0;
+  std::string err;
+  int64_t launches = 0;
+  void* encode_tiled = nullptr;  // PFN_cuTensorMapEncodeTiled
+};
+
+struct jegal_layout {
+  jegal_ctx* ctx = nullptr;
+  int32_t n_clips = 0;
+  int64_t rows = 0;
+  int32_t max_len = 0;
+  bool warp_aligned = false;  // every clip lies inside one aligned 32-row window
+  std::vector<int32_t> cu_host;
+  int32_t* cu_dev = nullptr;
+  int32_t* row2clip_dev = nullptr;
+  struct CTileSet {
+    int width = 0;
+    bool allow_split = false;
+    bool any_partial = false;
+    int n = 0;
+    std::vector<jegal::CTile> host;
+    jegal::CTile* dev = nullptr;
+  };
+  std::vector<CTileSet*> ctile_sets;
+};
+
+namespace jegal {
+
+int set_err(jegal_ctx* ctx, int code, const std::string& msg);
+#define JEGAL_CUDA_OK(ctx, expr)                                                        \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return ::jegal::set_err(ctx, JEGAL_ERR_CUDA,                                      \
+                              std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+
+// host-side launchers implemented in the kernel files
+int launch_simpool(jegal_ctx* ctx, int cta_group, int col_op, int row_op, const CUtensorMap& tmR,
+                   const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream);
+int launch_fill_f32(jegal_ctx* ctx, float* dst, int64_t n, float value, cudaStream_t stream);
+int launch_row2clip(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
+                    int32_t* row2clip_dev, cudaStream_t stream);
+int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int in_dtype,
+                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows,
+                float* inv_meannorm, cudaStream_t stream);
+int launch_topk(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
+                int32_t idx_offset, float* out_val, int32_t* out_idx, cudaStream_t stream);
+int launch_topk_merge(jegal_ctx* ctx, const float* vals, const int32_t* idxs, int32_t n_lists,
+                      int32_t n_q, int32_t k, float* out_val, int32_t* out_idx, cudaStream_t stream);
+int launch_rank_of_positive(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g,
+                            int64_t ld_row, int64_t ld_col, const int32_t* gt, int32_t* n_greater,
+                            int32_t* n_equal, cudaStream_t stream);
+
+int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows,
+                      int op_dtype);
+
+}  // namespace jegal

@@ -1,0 +1,201 @@
+// K0 — one pass over the embedding rows: L2-normalise in fp32, cast to the 16-bit
+// operand type the tensor cores consume, and (optionally) produce the per-clip
+// 1/||mean row|| scale that turns mean/mean pooling into the reference's
+// "cosine of mean-pooled embeddings" (evaluation/evaluate_retrieval.py:30-31,38-48;
+// evaluation/evaluate_asd.py:31-36,43-47).  HBM-bound: every input byte is read
+// once with 16-byte loads, every output byte written once with 16-byte stores.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "internal.h"
+
+namespace jegal {
+namespace {
+
+constexpr int kPrepWarps = 4;
+
+template <int kInDtype>
+__device__ __forceinline__ void load8(const void* base, int64_t row, int col, float (&x)[8]) {
+  if constexpr (kInDtype == JEGAL_F32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + row * kD + col);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + row * kD + col));
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (kInDtype == JEGAL_F16) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+        const float2 f = __half22float2(h);
+        x[2 * i] = f.x; x[2 * i + 1] = f.y;
+      } else {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        const float2 f = __bfloat1622float2(h);
+        x[2 * i] = f.x; x[2 * i + 1] = f.y;
+      }
+    }
+  }
+}
+
+template <int kOutDtype>
+__device__ __forceinline__ void store8(void* base, int64_t row, int col, const float (&x)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (kOutDtype == JEGAL_F16) {
+      const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + row * kD + col) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one block per clip; each warp walks the clip's rows with stride kPrepWarps
+template <int kInDtype, int kOutDtype>
+__global__ void __launch_bounds__(kPrepWarps * 32)
+prep_kernel(const void* __restrict__ emb, const int32_t* __restrict__ cu, int32_t n_clips,
+            int normalize_rows, float row_eps, float mean_eps, void* __restrict__ out,
+            float* __restrict__ inv_meannorm) {
+  __shared__ float colsum[kPrepWarps][kD];
+  __shared__ float red[kPrepWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool want_mean = inv_meannorm != nullptr;
+  for (int32_t clip = blockIdx.x; clip < n_clips; clip += gridDim.x) {
+    const int32_t r0 = __ldg(cu + clip), r1 = __ldg(cu + clip + 1);
+    float cs[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+    for (int32_t r = r0 + warp; r < r1; r += kPrepWarps) {
+      float a[8], b[8];
+      load8<kInDtype>(emb, r, lane * 8, a);
+      load8<kInDtype>(emb, r, 256 + lane * 8, b);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ss += a[i] * a[i] + b[i] * b[i];
+        cs[i] += a[i];
+        cs[8 + i] += b[i];
+      }
+      if (normalize_rows) {
+        ss = warp_sum(ss);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), row_eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] *= inv;
+          b[i] *= inv;
+        }
+      }
+      store8<kOutDtype>(out, r, lane * 8, a);
+      store8<kOutDtype>(out, r, 256 + lane * 8, b);
+    }
+    if (want_mean) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        colsum[warp][lane * 8 + i] = cs[i];
+        colsum[warp][256 + lane * 8 + i] = cs[8 + i];
+      }
+      __syncthreads();
+      const float inv_len = 1.0f / static_cast<float>(max(r1 - r0, 1));
+      float part = 0.f;
+      for (int c = threadIdx.x; c < kD; c += kPrepWarps * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kPrepWarps; ++w) s += colsum[w][c];
+        float m = s * inv_len;
+        // numpy's .mean(axis=0) of an fp16 array returns fp16 (fp32 accumulate): mirror that rounding
+        if constexpr (kInDtype == JEGAL_F16) m = __half2float(__float2half_rn(m));
+        part += m * m;
+      }
+      part = warp_sum(part);
+      if (lane == 0) red[warp] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < kPrepWarps; ++w) tot += red[w];
+        inv_meannorm[clip] = 1.0f / fmaxf(sqrtf(tot), mean_eps);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void row2clip_kernel(const int32_t* __restrict__ cu, int32_t n_clips, int64_t rows,
+                                int32_t* __restrict__ row2clip) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    int32_t lo = 0, hi = n_clips;  // invariant: cu[lo] <= r < cu[hi]
+    while (hi - lo > 1) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (__ldg(cu + mid) <= r) lo = mid; else hi = mid;
+    }
+    row2clip[r] = lo;
+  }
+}
+
+template <int kIn>
+int launch_prep_in(jegal_ctx* ctx, int out_dtype, dim3 grid, cudaStream_t stream, const void* emb,
+                   const int32_t* cu, int32_t n_clips, int normalize_rows, float row_eps,
+                   float mean_eps, void* out, float* inv_meannorm) {
+  if (out_dtype == JEGAL_BF16) {
+    prep_kernel<kIn, JEGAL_BF16><<<grid, kPrepWarps * 32, 0, stream>>>(
+        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm);
+  } else if (out_dtype == JEGAL_F16) {
+    prep_kernel<kIn, JEGAL_F16><<<grid, kPrepWarps * 32, 0, stream>>>(
+        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm);
+  } else {
+    return set_err(ctx, JEGAL_ERR_ARG, "prep: out_dtype must be JEGAL_BF16 or JEGAL_F16");
+  }
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // namespace
+
+int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int in_dtype,
+                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows,
+                float* inv_meannorm, cudaStream_t stream) {
+  if (layout->n_clips == 0) return JEGAL_OK;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 64;
+  const dim3 grid(static_cast<unsigned>(layout->n_clips < cap ? layout->n_clips : cap));
+  switch (in_dtype) {
+    case JEGAL_F32:
+      return launch_prep_in<JEGAL_F32>(ctx, out_dtype, grid, stream, emb, layout->cu_dev, layout->n_clips,
+                                       normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm);
+    case JEGAL_F16:
+      return launch_prep_in<JEGAL_F16>(ctx, out_dtype, grid, stream, emb, layout->cu_dev, layout->n_clips,
+                                       normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm);
+    case JEGAL_BF16:
+      return launch_prep_in<JEGAL_BF16>(ctx, out_dtype, grid, stream, emb, layout->cu_dev, layout->n_clips,
+                                        normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm);
+    default:
+      return set_err(ctx, JEGAL_ERR_ARG, "prep: bad in_dtype");
+  }
+}
+
+int launch_row2clip(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
+                    int32_t* row2clip_dev, cudaStream_t stream) {
+  if (rows <= 0) return JEGAL_OK;
+  const int threads = 256;
+  int64_t blocks = (rows + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 32;
+  if (blocks > cap) blocks = cap;
+  row2clip_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(cu_dev, n_clips, rows, row2clip_dev);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // namespace jegal

@@ -1,0 +1,477 @@
+// K1 — all-pairs fused similarity + pooling for sm_100a.
+//
+//   S = R . C^T  (R: "row operand" [rowsR, 512], C: "column operand" [rowsC, 512],
+//   both 16-bit, unit-norm rows, K-major) is formed tile by tile in tensor memory
+//   and pooled in the epilogue; S itself never reaches shared or global memory.
+//
+//   out[rclip * ld_r + cclip * ld_c] =
+//        rscale * cscale * ROWOP_{r in rclip} COLOP_{c in cclip} S[r, c]
+//
+// The host picks which of (gesture, content) is R and which is C so that the
+// FIRST pooling reduction runs along columns: TMEM lane = row = one thread, so a
+// column reduction is register-local (3-input FMNMX / FADD) and only the already
+// reduced value crosses lanes (segmented warp shuffles).
+//
+// Structure (one CTA per SM, or one CTA pair per two SMs with cta_group::2):
+//   - the column tile (128 rows of C per CTA, full K = 128 KB) is STATIONARY in
+//     shared memory; row tiles of R stream through a kStages-deep TMA ring
+//     (16 KB per k-block), so every MMA reads A and B from smem and L2->smem
+//     traffic per MMA tile is halved with respect to streaming both operands;
+//   - warp 0: TMA producer, warp 1: tcgen05.mma issuer, warp 2: TMEM allocator,
+//     warps 4-7: epilogue (tcgen05.ld -> pooling -> global);
+//   - two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs
+//     of tile i+1; stationary-tile k-blocks are released one by one during the
+//     last row tile of a unit so the next column tile's load overlaps too;
+//   - work is split over clusters by "row-tile steps" inside L2-sized phases of
+//     R so that all CTAs stream the same slice of R at the same time.
+#include <cstdio>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace jegal {
+
+using namespace ptx;
+
+namespace {
+
+constexpr uint32_t kTileBytes = kTileRows * kBlockK * 2;  // 16384
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int kOp>
+__device__ __forceinline__ float op_ident() {
+  return kOp == OP_MAX ? -INFINITY : 0.0f;
+}
+template <int kOp>
+__device__ __forceinline__ float op_apply(float a, float b) {
+  return kOp == OP_MAX ? fmaxf(a, b) : a + b;
+}
+
+template <int kOp>
+__device__ __forceinline__ float reduce8(const uint32_t* v) {
+  if constexpr (kOp == OP_MAX) {
+    float m1 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    float m2 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    return fmax3(m1, m2, fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+  } else {
+    float s0 = __uint_as_float(v[0]) + __uint_as_float(v[1]);
+    float s1 = __uint_as_float(v[2]) + __uint_as_float(v[3]);
+    float s2 = __uint_as_float(v[4]) + __uint_as_float(v[5]);
+    float s3 = __uint_as_float(v[6]) + __uint_as_float(v[7]);
+    return (s0 + s1) + (s2 + s3);
+  }
+}
+
+// Work iterator shared by all warp roles: every role walks the same sequence of
+// units (column tile ct, row tiles [rt0, rt0 + nrt)).
+struct UnitIter {
+  int32_t n_ctiles, n_rtiles, chunk;
+  uint32_t cid, ncl;
+  int32_t m0, cm;
+  int64_t s, hi;
+  __device__ UnitIter(const SimpoolParams& p, uint32_t cluster, uint32_t nclusters)
+      : n_ctiles(p.n_ctiles), n_rtiles(p.n_rtiles), chunk(p.chunk_rtiles), cid(cluster),
+        ncl(nclusters), m0(-p.chunk_rtiles), cm(1), s(0), hi(0) {}
+  __device__ bool next(int32_t& ct, int32_t& rt0, int32_t& nrt) {
+    while (s >= hi) {
+      m0 += chunk;
+      if (m0 >= n_rtiles) return false;
+      cm = min(chunk, n_rtiles - m0);
+      const int64_t steps = static_cast<int64_t>(n_ctiles) * cm;
+      s = steps * cid / ncl;
+      hi = steps * (cid + 1) / ncl;
+    }
+    ct = static_cast<int32_t>(s / cm);
+    const int32_t mt = static_cast<int32_t>(s - static_cast<int64_t>(ct) * cm);
+    const int64_t run_end = min(hi, static_cast<int64_t>(ct + 1) * cm);
+    rt0 = m0 + mt;
+    nrt = static_cast<int32_t>(run_end - s);
+    s = run_end;
+    return true;
+  }
+};
+
+struct RowCtx {
+  int32_t rclip;
+  float rscale;
+  uint32_t same;  // bit k: lane + 2^k is in the same row segment
+  bool head;      // first lane of its segment within the warp
+  bool complete;  // the whole clip lies inside this warp's 32 rows
+};
+
+template <int kColOp, int kRowOp>
+__device__ __forceinline__ void emit(float acc, int32_t cclip, bool col_partial, const RowCtx& rc,
+                                     const SimpoolParams& p) {
+  float v = rc.rclip >= 0 ? acc * rc.rscale : op_ident<kRowOp>();
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float o = __shfl_down_sync(0xffffffffu, v, 1u << k);
+    if ((rc.same >> k) & 1u) v = op_apply<kRowOp>(v, o);
+  }
+  if (rc.head) {
+    float sc = p.cscale ? __ldg(p.cscale + cclip) : 1.0f;
+    if constexpr (kColOp == OP_SUM) {
+      const int32_t len = __ldg(p.cu_C + cclip + 1) - __ldg(p.cu_C + cclip);
+      sc *= 1.0f / static_cast<float>(len);
+    }
+    const float val = v * sc;
+    float* dst = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r + static_cast<int64_t>(cclip) * p.ld_c;
+    if (rc.complete && !col_partial) {
+      *dst = val;
+    } else if constexpr (kRowOp == OP_MAX) {
+      atomic_max_f32(dst, val);
+    } else {
+      atomicAdd(dst, val);
+    }
+  }
+}
+
+template <int kCG, int kStages, int kColOp, int kRowOp>
+__global__ void __launch_bounds__(kThreads, 1)
+simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
+               const SimpoolParams p) {
+  constexpr int UMMA_M = kTileRows * kCG;
+  constexpr int UMMA_N = kTileRows * kCG;
+  constexpr uint32_t kTmemCols = 2 * UMMA_N;
+  constexpr int NKB = kNumKBlocks;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t smC = base;
+  const uint32_t smR = base + NKB * kTileBytes;
+  const uint32_t bars = smR + kStages * kTileBytes;
+  auto r_full = [&](int i) { return bars + 8u * i; };
+  auto r_empty = [&](int i) { return bars + 8u * (kStages + i); };
+  auto c_full = [&](int k) { return bars + 8u * (2 * kStages + k); };
+  auto c_empty = [&](int k) { return bars + 8u * (2 * kStages + NKB + k); };
+  auto t_full = [&](int b) { return bars + 8u * (2 * kStages + 2 * NKB + b); };
+  auto t_empty = [&](int b) { return bars + 8u * (2 * kStages + 2 * NKB + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 2 * NKB + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t cluster = kCG == 2 ? cluster_id_x() : blockIdx.x;
+  const uint32_t nclusters = kCG == 2 ? num_clusters_x() : gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmR);
+    prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(r_full(i), 1);
+      mbar_init(r_empty(i), 1);
+    }
+    for (int k = 0; k < NKB; ++k) {
+      mbar_init(c_full(k), 1);
+      mbar_init(c_empty(k), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full(b), 1);
+      mbar_init(t_empty(b), 4 * kCG);  // one arrival per epilogue warp of every CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kCG>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  if constexpr (kCG == 2) {
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      const uint64_t pol_R = policy_evict_last();    // R chunk is re-streamed by every unit
+      const uint64_t pol_C = policy_evict_normal();
+      UnitIter it(p, cluster, nclusters);
+      int32_t ct, rt0, nrt;
+      uint32_t rs = 0, rphase = 0, unit = 0;
+      while (it.next(ct, rt0, nrt)) {
+        const int32_t c_row = __ldg(&p.ctiles[ct].row0) + static_cast<int32_t>(rank) * kTileRows;
+        for (int32_t t = 0; t < nrt; ++t) {
+          const int32_t r_row = (rt0 + t) * UMMA_M + static_cast<int32_t>(rank) * kTileRows;
+          for (int kb = 0; kb < NKB; ++kb) {
+            if (t == 0) {
+              // (re)load stationary k-block kb once the previous unit's MMAs released it
+              if (unit > 0) mbar_wait(c_empty(kb), (unit - 1) & 1u);
+              if constexpr (kCG == 2) {
+                if (rank == 0) mbar_arrive_expect_tx(c_full(kb), kTileBytes * 2);
+                tma_load_2d_pair(&tmC, c_full(kb) & kPeerBitMask, smC + kb * kTileBytes,
+                                 kb * kBlockK, c_row, pol_C);
+              } else {
+                mbar_arrive_expect_tx(c_full(kb), kTileBytes);
+                tma_load_2d(&tmC, c_full(kb), smC + kb * kTileBytes, kb * kBlockK, c_row, pol_C);
+              }
+            }
+            mbar_wait(r_empty(rs), rphase ^ 1u);
+            if constexpr (kCG == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(r_full(rs), kTileBytes * 2);
+              tma_load_2d_pair(&tmR, r_full(rs) & kPeerBitMask, smR + rs * kTileBytes, kb * kBlockK,
+                               r_row, pol_R);
+            } else {
+              mbar_arrive_expect_tx(r_full(rs), kTileBytes);
+              tma_load_2d(&tmR, r_full(rs), smR + rs * kTileBytes, kb * kBlockK, r_row, pol_R);
+            }
+            if (++rs == kStages) {
+              rs = 0;
+              rphase ^= 1u;
+            }
+          }
+        }
+        ++unit;
+      }
+      // producer tail: do not leave while tcgen05.commit arrivals may still be in
+      // flight towards this CTA's barriers (the peer CTA of a pair must stay alive).
+      if (unit > 0) {
+        for (int i = 0; i < kStages; ++i) {
+          mbar_wait(r_empty(rs), rphase ^ 1u);
+          if (++rs == kStages) {
+            rs = 0;
+            rphase ^= 1u;
+          }
+        }
+        for (int kb = 0; kb < NKB; ++kb) mbar_wait(c_empty(kb), (unit - 1) & 1u);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (rank == 0 && elect_one()) {
+      UnitIter it(p, cluster, nclusters);
+      int32_t ct, rt0, nrt;
+      uint32_t rs = 0, rphase = 0, unit = 0, tile = 0;
+      const uint64_t descC0 = make_smem_desc_sw128(smC);
+      const uint64_t descR0 = make_smem_desc_sw128(smR);
+      while (it.next(ct, rt0, nrt)) {
+        for (int32_t t = 0; t < nrt; ++t, ++tile) {
+          const uint32_t buf = tile & 1u;
+          mbar_wait(t_empty(buf), ((tile >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * UMMA_N;
+          for (int kb = 0; kb < NKB; ++kb) {
+            if (t == 0) mbar_wait(c_full(kb), unit & 1u);
+            mbar_wait(r_full(rs), rphase);
+            tc_fence_after();
+            const uint64_t dR = descR0 + static_cast<uint64_t>((rs * kTileBytes) >> 4);
+            const uint64_t dC = descC0 + static_cast<uint64_t>((kb * kTileBytes) >> 4);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 bytes (2 x 16 B) per 16-element K step inside the 128 B swizzle row
+              umma_f16<kCG>(d_tmem, dR + 2u * k, dC + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<kCG>(r_empty(rs));
+            if (t == nrt - 1) umma_commit<kCG>(c_empty(kb));
+            if (++rs == kStages) {
+              rs = 0;
+              rphase ^= 1u;
+            }
+          }
+          umma_commit<kCG>(t_full(buf));
+        }
+        ++unit;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp - kEpiWarp0;  // TMEM lane quarter == warp % 4
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    UnitIter it(p, cluster, nclusters);
+    int32_t ct, rt0, nrt;
+    uint32_t tile = 0;
+    while (it.next(ct, rt0, nrt)) {
+      const CTile* ctile = p.ctiles + ct;
+      const int32_t n_valid = __ldg(&ctile->n_valid);
+      const int32_t clip0 = __ldg(&ctile->clip0);
+      const bool col_partial = __ldg(&ctile->partial) != 0;
+      const uint32_t my_em = lane < 8 ? __ldg(&ctile->endmask[lane]) : 0u;
+      const int nchunks = (n_valid + 31) >> 5;
+      for (int32_t t = 0; t < nrt; ++t, ++tile) {
+        // per-row context for this tile (loads overlap the wait for the accumulator)
+        RowCtx rc;
+        {
+          const int32_t row = (rt0 + t) * UMMA_M + static_cast<int32_t>(rank) * kTileRows + q * 32 + lane;
+          rc.rclip = row < p.n_rows_R ? __ldg(p.row2clip_R + row) : -1;
+          int32_t sb = 0, se = 1;
+          if (rc.rclip >= 0) {
+            sb = __ldg(p.cu_R + rc.rclip);
+            se = __ldg(p.cu_R + rc.rclip + 1);
+          }
+          float rs_ = (rc.rclip >= 0 && p.rscale) ? __ldg(p.rscale + rc.rclip) : 1.0f;
+          if constexpr (kRowOp == OP_SUM) rs_ *= 1.0f / static_cast<float>(se - sb);
+          rc.rscale = rs_;
+          rc.same = 0;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int32_t o = __shfl_down_sync(0xffffffffu, rc.rclip, 1u << k);
+            if (lane + (1 << k) < 32 && o == rc.rclip) rc.same |= 1u << k;
+          }
+          const int32_t prev = __shfl_up_sync(0xffffffffu, rc.rclip, 1);
+          rc.head = rc.rclip >= 0 && (lane == 0 || prev != rc.rclip);
+          const int32_t wrow0 = row - lane;
+          rc.complete = sb >= wrow0 && se <= wrow0 + 32;
+        }
+        const uint32_t buf = tile & 1u;
+        mbar_wait(t_full(buf), (tile >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + lane_off + buf * UMMA_N;
+
+        float acc = op_ident<kColOp>();
+        int32_t cclip = clip0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == nchunks - 1) {
+            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCG == 2) {
+                mbar_arrive_cluster(t_empty(buf) & kPeerBitMask);
+              } else {
+                mbar_arrive(t_empty(buf));
+              }
+            }
+          }
+          const uint32_t em = __shfl_sync(0xffffffffu, my_em, ch);
+          if ((em & 0x7f7f7f7fu) == 0u) {
+            // fast path: segment ends (if any) only at columns 7/15/23/31 of the chunk
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
+              if ((em >> (8 * j + 7)) & 1u) {
+                emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+                ++cclip;
+                acc = op_ident<kColOp>();
+              }
+            }
+          } else {
+            // general path: one masked reduction per run of columns between segment ends
+            uint32_t rem = em;
+            uint32_t start = 0;
+            while (true) {
+              const uint32_t e = rem ? static_cast<uint32_t>(__ffs(rem) - 1) : 31u;
+              const uint32_t m = (e == 31u ? 0xffffffffu : ((1u << (e + 1)) - 1u)) & ~((1u << start) - 1u);
+              float r = op_ident<kColOp>();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = ((m >> j) & 1u) ? __uint_as_float(v[j]) : op_ident<kColOp>();
+                r = op_apply<kColOp>(r, x);
+              }
+              acc = op_apply<kColOp>(acc, r);
+              if (!rem) break;
+              emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+              ++cclip;
+              acc = op_ident<kColOp>();
+              rem &= rem - 1u;
+              start = e + 1u;
+              if (start >= 32u) break;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  if constexpr (kCG == 2) {
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
+  if (warp == 2) tmem_dealloc<kCG>(tmem_base, kTmemCols);
+}
+
+template <int kCG, int kStages>
+constexpr size_t simpool_smem_bytes() {
+  return 1024 /*alignment slack*/ + static_cast<size_t>(kNumKBlocks + kStages) * kTileBytes +
+         8 * (2 * kStages + 2 * kNumKBlocks + 4) + 16;
+}
+
+constexpr int kStagesDefault = 5;
+
+template <int kCG, int kColOp, int kRowOp>
+int launch_simpool_t(jegal_ctx* ctx, const CUtensorMap& tmR, const CUtensorMap& tmC,
+                     const SimpoolParams& p, cudaStream_t stream) {
+  auto kern = simpool_kernel<kCG, kStagesDefault, kColOp, kRowOp>;
+  constexpr size_t smem = simpool_smem_bytes<kCG, kStagesDefault>();
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+    configured = true;
+  }
+  const int64_t steps = static_cast<int64_t>(p.n_ctiles) * p.n_rtiles;
+  int nclusters = ctx->sm_count / kCG;
+  if (steps < nclusters) nclusters = static_cast<int>(steps > 0 ? steps : 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(nclusters * kCG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  JEGAL_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, tmR, tmC, p));
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+template <int kCG>
+int launch_simpool_cg(jegal_ctx* ctx, int col_op, int row_op, const CUtensorMap& tmR,
+                      const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream) {
+  if (col_op == OP_SUM && row_op == OP_SUM)
+    return launch_simpool_t<kCG, OP_SUM, OP_SUM>(ctx, tmR, tmC, p, stream);
+  if (col_op == OP_MAX && row_op == OP_SUM)
+    return launch_simpool_t<kCG, OP_MAX, OP_SUM>(ctx, tmR, tmC, p, stream);
+  if (col_op == OP_MAX && row_op == OP_MAX)
+    return launch_simpool_t<kCG, OP_MAX, OP_MAX>(ctx, tmR, tmC, p, stream);
+  return set_err(ctx, JEGAL_ERR_ARG, "simpool: unsupported (col_op,row_op)");
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float value) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t n4 = n >> 2;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4 v4 = make_float4(value, value, value, value);
+  for (int64_t i = i0; i < n4; i += stride) d4[i] = v4;
+  for (int64_t i = (n4 << 2) + i0; i < n; i += stride) dst[i] = value;
+}
+
+}  // namespace
+
+int launch_simpool(jegal_ctx* ctx, int cta_group, int col_op, int row_op, const CUtensorMap& tmR,
+                   const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream) {
+  if (cta_group == 2) return launch_simpool_cg<2>(ctx, col_op, row_op, tmR, tmC, p, stream);
+  if (cta_group == 1) return launch_simpool_cg<1>(ctx, col_op, row_op, tmR, tmC, p, stream);
+  return set_err(ctx, JEGAL_ERR_ARG, "simpool: cta_group must be 1 or 2");
+}
+
+int launch_fill_f32(jegal_ctx* ctx, float* dst, int64_t n, float value, cudaStream_t stream) {
+  if (n <= 0) return JEGAL_OK;
+  const int threads = 256;
+  int64_t blocks = (n / 4 + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  fill_f32_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(dst, n, value);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // namespace jegal

@@ -1,0 +1,203 @@
+// K2 — per-query top-k, k-way merge of per-shard lists, and rank-of-positive.
+// These replace the full np.sort(-x, axis=1) + diagonal lookup of
+// compute_metrics (evaluation/evaluate_retrieval.py:51-65).  All three stream a
+// dense fp32 score matrix once with 16-byte loads: HBM-bound.
+//
+// Ordering rule everywhere: descending score, ties towards the LOWER index, so a
+// gallery sharded over several GPUs merges to exactly the single-GPU list.
+#include "internal.h"
+
+namespace jegal {
+namespace {
+
+constexpr int kTopkWarps = 8;
+
+__device__ __forceinline__ bool better(float av, int32_t ai, float bv, int32_t bi) {
+  return av > bv || (av == bv && ai < bi);
+}
+
+// A warp holds a descending list of 32 (value, index) items, one per lane.
+struct WarpList {
+  float v;
+  int32_t i;
+  __device__ __forceinline__ void init() {
+    v = -INFINITY;
+    i = 0x7fffffff;
+  }
+  // insert (cv, ci) — warp-uniform arguments — which must beat lane 31's item
+  __device__ __forceinline__ void insert(float cv, int32_t ci, int lane) {
+    const bool worse = better(cv, ci, v, i);
+    const uint32_t wm = __ballot_sync(0xffffffffu, worse);
+    const int pos = __ffs(wm) - 1;
+    const float upv = __shfl_up_sync(0xffffffffu, v, 1);
+    const int32_t upi = __shfl_up_sync(0xffffffffu, i, 1);
+    if (pos >= 0) {
+      if (lane > pos) {
+        v = upv;
+        i = upi;
+      } else if (lane == pos) {
+        v = cv;
+        i = ci;
+      }
+    }
+  }
+  // offer one candidate per lane; candidates that beat the current k-th item get inserted
+  __device__ __forceinline__ void offer(float cv, int32_t ci, bool valid, int k, int lane) {
+    float tv = __shfl_sync(0xffffffffu, v, k - 1);
+    int32_t ti = __shfl_sync(0xffffffffu, i, k - 1);
+    uint32_t m = __ballot_sync(0xffffffffu, valid && better(cv, ci, tv, ti));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float bv = __shfl_sync(0xffffffffu, cv, src);
+      const int32_t bi = __shfl_sync(0xffffffffu, ci, src);
+      if (better(bv, bi, tv, ti)) {
+        insert(bv, bi, lane);
+        tv = __shfl_sync(0xffffffffu, v, k - 1);
+        ti = __shfl_sync(0xffffffffu, i, k - 1);
+      }
+    }
+  }
+};
+
+// one block per query row
+__global__ void __launch_bounds__(kTopkWarps * 32)
+topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k, int32_t idx_offset,
+            float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  __shared__ float sv[kTopkWarps][32];
+  __shared__ int32_t si[kTopkWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = blockIdx.x;
+  const float* row = scores + q * ld;
+  WarpList L;
+  L.init();
+  // vector body: needs a 16-byte aligned row start
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+  const int32_t n4 = vec_ok ? (n_g >> 2) : 0;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  for (int32_t base = warp * 32; base < n4; base += kTopkWarps * 32) {
+    const int32_t j4 = base + lane;
+    const bool valid = j4 < n4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) x = __ldg(row4 + j4);
+    const int32_t j = j4 * 4;
+    L.offer(x.x, j + 0, valid, k, lane);
+    L.offer(x.y, j + 1, valid, k, lane);
+    L.offer(x.z, j + 2, valid, k, lane);
+    L.offer(x.w, j + 3, valid, k, lane);
+  }
+  for (int32_t base = n4 * 4 + warp * 32; base < n_g; base += kTopkWarps * 32) {
+    const int32_t j = base + lane;
+    const bool valid = j < n_g;
+    const float x = valid ? __ldg(row + j) : 0.f;
+    L.offer(x, j, valid, k, lane);
+  }
+  sv[warp][lane] = L.v;
+  si[warp][lane] = L.i;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kTopkWarps; ++w) L.offer(sv[w][lane], si[w][lane], lane < k, k, lane);
+    if (lane < k) {
+      const bool real = L.i != 0x7fffffff;
+      out_val[q * k + lane] = L.v;
+      out_idx[q * k + lane] = real ? L.i + idx_offset : -1;
+    }
+  }
+}
+
+// one warp per query: merge n_lists lists of k
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idxs, int32_t n_lists,
+                  int32_t n_q, int32_t k, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_q) return;
+  WarpList L;
+  L.init();
+  for (int32_t l = 0; l < n_lists; ++l) {
+    const int64_t off = (static_cast<int64_t>(l) * n_q + q) * k;
+    const bool valid = lane < k;
+    float cv = valid ? __ldg(vals + off + lane) : 0.f;
+    int32_t ci = valid ? __ldg(idxs + off + lane) : 0;
+    const bool real = valid && ci >= 0;
+    L.offer(cv, ci, real, k, lane);
+  }
+  if (lane < k) {
+    const bool real = L.i != 0x7fffffff;
+    out_val[static_cast<int64_t>(q) * k + lane] = L.v;
+    out_idx[static_cast<int64_t>(q) * k + lane] = real ? L.i : -1;
+  }
+}
+
+// one block per row: counts of entries strictly greater than / equal to the positive
+__global__ void __launch_bounds__(256)
+rank_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld_row, int64_t ld_col,
+            const int32_t* __restrict__ gt, int32_t* __restrict__ n_greater, int32_t* __restrict__ n_equal) {
+  __shared__ int32_t sg[8], se[8];
+  const int64_t q = blockIdx.x;
+  const int32_t g = gt ? __ldg(gt + q) : static_cast<int32_t>(q);
+  const float* row = scores + q * ld_row;
+  const float pos = __ldg(row + static_cast<int64_t>(g) * ld_col);
+  int32_t cg = 0, ce = 0;
+  for (int32_t j = threadIdx.x; j < n_g; j += blockDim.x) {
+    const float x = __ldg(row + static_cast<int64_t>(j) * ld_col);
+    cg += x > pos;
+    ce += x == pos;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cg += __shfl_xor_sync(0xffffffffu, cg, o);
+    ce += __shfl_xor_sync(0xffffffffu, ce, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sg[warp] = cg;
+    se[warp] = ce;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t tg = 0, te = 0;
+    for (int w = 0; w < 8; ++w) {
+      tg += sg[w];
+      te += se[w];
+    }
+    n_greater[q] = tg;
+    if (n_equal) n_equal[q] = te;
+  }
+}
+
+}  // namespace
+
+int launch_topk(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
+                int32_t idx_offset, float* out_val, int32_t* out_idx, cudaStream_t stream) {
+  if (n_q <= 0) return JEGAL_OK;
+  topk_kernel<<<static_cast<unsigned>(n_q), kTopkWarps * 32, 0, stream>>>(scores, n_g, ld, k, idx_offset,
+                                                                        out_val, out_idx);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+int launch_topk_merge(jegal_ctx* ctx, const float* vals, const int32_t* idxs, int32_t n_lists,
+                      int32_t n_q, int32_t k, float* out_val, int32_t* out_idx, cudaStream_t stream) {
+  if (n_q <= 0) return JEGAL_OK;
+  const int warps = 4;
+  const unsigned blocks = static_cast<unsigned>((n_q + warps - 1) / warps);
+  topk_merge_kernel<<<blocks, warps * 32, 0, stream>>>(vals, idxs, n_lists, n_q, k, out_val, out_idx);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+int launch_rank_of_positive(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g,
+                            int64_t ld_row, int64_t ld_col, const int32_t* gt, int32_t* n_greater,
+                            int32_t* n_equal, cudaStream_t stream) {
+  if (n_q <= 0) return JEGAL_OK;
+  rank_kernel<<<static_cast<unsigned>(n_q), 256, 0, stream>>>(scores, n_g, ld_row, ld_col, gt, n_greater,
+                                                             n_equal);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // namespace jegal
