@@ -109,7 +109,8 @@ def stage_simpool_small():
     g = _rand_clips(8, 64, 64, 2)
     c = _rand_clips(40, 16, 16, 3)
     ok &= _check_simpool(g, c, ["max_t_mean_w", "mean_mean", "max_w_mean_t", "max_max"], tag="uniform")
-    g = _rand_clips(33, 25, 200, 4)
+    tmax = 120 if os.environ.get("JEGAL_CTA_GROUP") == "1" else 200
+    g = _rand_clips(33, 25, tmax, 4)
     c = _rand_clips(45, 4, 40, 5)
     ok &= _check_simpool(g, c, ["max_t_mean_w", "mean_mean", "max_w_mean_t", "max_max"], tag="ragged")
     g = _rand_clips(5, 1, 3, 6)
@@ -123,7 +124,8 @@ def stage_simpool_small():
 
 
 def stage_simpool_mid():
-    g = _rand_clips(300, 25, 200, 10)
+    tmax = 120 if os.environ.get("JEGAL_CTA_GROUP") == "1" else 200
+    g = _rand_clips(300, 25, tmax, 10)
     c = _rand_clips(300, 4, 40, 11)
     assert _check_simpool(g, c, ["max_t_mean_w", "mean_mean", "max_w_mean_t", "max_max"], tag="mid")
     print("simpool_mid OK")
