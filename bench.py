@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the JEGAL cross-modal scoring path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg2]
+
+One "step" = one pass of the hot path over one batch of synthetic embeddings:
+    raw fp16 embeddings -> K0 normalise+cast -> K1 fused T x W cosine + pooling (tcgen05)
+    -> K2 per-query top-k (-> all-gather + merge when the gallery is sharded over N GPUs).
+
+Workload (BASELINE.json configs[4], the configuration the metric and the 1/2/4/8-GPU target
+are quoted on; it fits one GPU): 1000 query clips (T = 64 frames) against a 65 536-clip
+gallery (W = 16 words), D = 512, pooling max over frames then mean over words, top-10.
+The gallery is sharded by clip over the N GPUs (strong scaling: total work is fixed).
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "clip-pair scores/sec (TxW sim-pool, D=512)"
+UNIT = "pair-scores/s"
+
+WORKLOADS = {
+    # name: (n_query, T, n_gallery, W, mode, k)
+    "cfg5": dict(Q=1000, T=64, G=65536, W=16, mode="max_t_mean_w", k=10,
+                 desc="large-gallery retrieval: 1000 queries (T=64) x 65536-clip gallery (W=16), D=512, "
+                      "max_t_mean_w pooling, top-10"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d["bf16_tflops"]), tflops_sustained=float(d.get("bf16_tflops_sustained", 0)),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_simpool_topk(q: torch.Tensor, g: torch.Tensor, Q: int, T: int, G: int, W: int, mode: str, k: int):
+    """The oracle's fp32 restatement (oracle/oracle.py: F.normalize + mm + amax/mean + topk),
+    chunked over queries so the T x W tiles fit in memory."""
+    from oracle import oracle
+
+    qn = oracle.normalize_rows(q)
+    gn = oracle.normalize_rows(g)
+    out = torch.empty((Q, G), dtype=torch.float32)
+    step = max(1, min(Q, (1 << 28) // max(1, T * G * W)))  # ~1 GB of fp32 tiles per chunk
+    for q0 in range(0, Q, step):
+        q1 = min(Q, q0 + step)
+        s = (qn[q0 * T:q1 * T] @ gn.t()).view(q1 - q0, T, G, W)
+        if mode == "max_t_mean_w":
+            out[q0:q1] = s.amax(dim=1).mean(dim=-1)
+        elif mode == "max_w_mean_t":
+            out[q0:q1] = s.amax(dim=3).mean(dim=1)
+        elif mode == "max_max":
+            out[q0:q1] = s.amax(dim=(1, 3))
+        else:
+            out[q0:q1] = s.mean(dim=(1, 3))
+    return oracle.topk(out.numpy(), k)
+
+
+def run_cpu_sample(wl: dict, g_sample: int, steps: int, warmup: int):
+    """Time the CPU port on `g_sample` gallery clips per step (same queries, same shapes)."""
+    from jegal_b200 import synth
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    q, g, _ = synth.cfg5_gallery(wl["Q"], g_sample, wl["T"], wl["W"], seed=1239, device="cpu")
+    for _ in range(warmup):
+        cpu_simpool_topk(q, g, wl["Q"], wl["T"], g_sample, wl["W"], wl["mode"], wl["k"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_simpool_topk(q, g, wl["Q"], wl["T"], g_sample, wl["W"], wl["mode"], wl["k"])
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return wl["Q"] * g_sample / dt, dt
+
+
+def main_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 1024))
+    cores = os.cpu_count() or 1
+    value, dt = run_cpu_sample(wl, g_sample, args.steps, args.warmup)
+    sample = (f"{wl['Q']} queries x {g_sample} gallery clips per step (same T/W/D/pooling/top-k), "
+              f"fp32 torch CPU, {torch.get_num_threads()} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "note": "the reference is pure Python/torch-CPU and cannot travel to "
+                   "the GPU box; this arm times the oracle port of its scoring arithmetic on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main_ours(args, wl, rank, local_rank, world):
+    from jegal_b200 import ops, sharded, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = ops.Context.get(local_rank)
+    Q, T, G, W, mode, k = wl["Q"], wl["T"], wl["G"], wl["W"], wl["mode"], wl["k"]
+    weak = args.scaling == "weak"
+    G_total = G * world if weak else G
+
+    # synthetic embeddings, generated on the device (identical on every rank: same seed)
+    lo, hi = sharded.shard_range(G_total, rank, world)
+    q_raw, g_all, gt = synth.cfg5_gallery(Q, G_total, T, W, seed=1239, device=dev) if world == 1 else (None, None, None)
+    if world > 1:
+        # every rank generates only what it owns: queries on rank 0, its own gallery shard
+        q_full, _, _ = synth.cfg5_gallery(Q, 16, T, W, seed=1239, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(1239 + 1000 * (rank + 1))
+        g_shard = torch.nn.functional.normalize(
+            torch.randn(((hi - lo) * W, 512), device=dev, generator=gen), dim=-1).half()
+        q_raw = q_full if rank == 0 else torch.empty_like(q_full)
+    else:
+        g_shard = g_all
+    n_shard = hi - lo
+    q_layout = ops.Layout.from_lengths([T] * Q)
+    s_layout = ops.Layout.from_lengths([W] * n_shard)
+    q16 = torch.empty((Q * T, 512), dtype=torch.bfloat16, device=dev)
+    g16 = torch.empty((n_shard * W, 512), dtype=torch.bfloat16, device=dev)
+    scores = torch.empty((Q, n_shard), dtype=torch.float32, device=dev)
+    ev_k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+             for _ in range(args.steps)]
+
+    def step(i_timed=None):
+        qr = sharded.broadcast_queries(q_raw, Q * T, torch.float16, dev) if world > 1 else q_raw
+        ops.prep(qr, q_layout, out=q16)
+        ops.prep(g_shard, s_layout, out=g16)
+        if i_timed is not None:
+            ev_k1[i_timed][0].record()
+        ops.simpool_allpairs(q16, q_layout, g16, s_layout, mode, out=scores)
+        if i_timed is not None:
+            ev_k1[i_timed][1].record()
+        v, i = ops.topk(scores, k, idx_offset=lo)
+        if world > 1:
+            vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
+            idxs = torch.empty((world * Q, k), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(vals, v)
+            dist.all_gather_into_tensor(idxs, i)
+            v, i = ops.topk_merge(vals.view(world, Q, k), idxs.view(world, Q, k))
+        return v, i
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for s in range(args.steps):
+        v, i = step(s)
+    e1.record()
+    sync_all()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_k1]))
+    t = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=dev)
+    lc = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lc, op=dist.ReduceOp.SUM)
+    ms_total, k1_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = Q * G_total / (ms_step * 1e-3)
+
+    # ---- end to end through the public host API: pinned host buffers in, top-k on the host out
+    from jegal_b200 import scoring
+
+    q_host = q_raw.cpu().pin_memory() if rank == 0 or world == 1 else None
+    g_host = g_shard.cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = g_host.numel() * 2 + (Q * T * 512 * 2 if (rank == 0 or world == 1) else 0)
+    d2h = Q * k * 8
+
+    def e2e_step():
+        g_dev = g_host.to(dev, non_blocking=True)
+        if world > 1:
+            q_dev = q_host.to(dev, non_blocking=True) if rank == 0 else torch.empty((Q * T, 512), dtype=torch.float16, device=dev)
+            dist.broadcast(q_dev, src=0)
+        else:
+            q_dev = q_host.to(dev, non_blocking=True)
+        ops.prep(q_dev, q_layout, out=q16)
+        ops.prep(g_dev, s_layout, out=g16)
+        ops.simpool_allpairs(q16, q_layout, g16, s_layout, mode, out=scores)
+        vv, ii = ops.topk(scores, k, idx_offset=lo)
+        if world > 1:
+            vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
+            idxs = torch.empty((world * Q, k), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(vals, vv)
+            dist.all_gather_into_tensor(idxs, ii)
+            vv, ii = ops.topk_merge(vals.view(world, Q, k), idxs.view(world, Q, k))
+        return vv.cpu(), ii.cpu()  # device->host read of the step's result (synchronises)
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hv, hi_ = e2e_step()
+    sync_all()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    hb = torch.tensor([h2d], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+    e2e_value = Q * G_total / float(te[0])
+
+    if rank != 0:
+        return
+    # sanity: with one GPU the planted matches must be retrieved (the bench measures real work)
+    recall1 = None
+    if world == 1 and gt is not None:
+        recall1 = float((i[:, 0].cpu().numpy() == gt).mean())
+    peaks = load_peaks()
+    flops = 2.0 * 512 * (Q * T) * (n_shard * W)  # algorithmic flops of ONE K1 launch on this rank's shard
+    achieved = flops / (k1_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": wl["desc"] + (f"; gallery x{world} (weak)" if weak else "; gallery sharded by clip over the GPUs"),
+            "step": "K0 prep(queries)+K0 prep(gallery shard)+K1 fused sim-pool+K2 top-k" + ("+all-gather+merge" if world > 1 else ""),
+            "inputs": "raw fp16 unit-norm embeddings resident in HBM; bf16 operands, fp32 accumulate in TMEM",
+            "l2": "no flush needed: the 1.07 GB gallery (>= 134 MB per shard) exceeds the 126 MB L2 every step",
+            "parallelism": f"gallery-sharded x{world}", "recall_at_1_planted": recall1,
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(te[0]) * 1e3, "steps": e2e_steps,
+                "path": "pinned host fp16 embeddings -> H2D -> K0/K1/K2 -> top-k (values, indices) -> host"},
+        "gpu_launches": int(lc[0]),
+        "roofline": {"bound": "tensor", "kernel": "simpool_kernel (K1)", "achieved": achieved, "peak": peaks["tflops"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                     "frac_of_sustained": achieved / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None,
+                     "peak_source": peaks["source"] + ", burst bf16 figure", "k1_ms": k1_ms,
+                     "algorithmic_flops_per_launch": flops, "traffic": None},
+    }
+    if world == 1 and not args.no_cpu:
+        g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 1024))
+        n_rep = 3
+        cv, cdt = run_cpu_sample(wl, g_sample, n_rep, 1)
+        line["cpu_baseline"] = {
+            "value": cv, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{Q} queries x {g_sample} gallery clips (1/{G // g_sample} of the gallery), {n_rep} timed "
+                      f"repeats of {cdt:.2f} s, fp32 torch CPU restatement (oracle), {torch.get_num_threads()} threads"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        main_reference(args, wl, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        main_ours(args, wl, rank, local_rank, world)
+    finally:
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -86,10 +86,12 @@ int32_t jegal_layout_clips(const jegal_layout* layout);
  *   normalize_rows 1: out row = row / max(||row||, row_eps) (fp32 math), 0: cast only
  *   out_rows_dev   [rows, 512] in `out_dtype` (JEGAL_BF16 or JEGAL_F16)
  *   inv_meannorm_dev (nullable) [n_clips] fp32: 1 / max(||mean of the clip's INPUT rows||, mean_eps)
+ *   mean_rows_dev  (nullable) [n_clips, 512] in `out_dtype`: mean row / max(||mean row||, mean_eps),
+ *                  i.e. the clip-level embedding evaluate_retrieval.py:30-31,41 feeds to its matmul
  */
 int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype,
                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
-               float* inv_meannorm_dev, void* stream);
+               float* inv_meannorm_dev, void* mean_rows_dev, void* stream);
 
 /* K1 — all-pairs fused similarity + pooling (tcgen05 / TMEM / TMA).
  * scores[g * ld_g + c * ld_c] = gscale[g] * cscale[c] * pool_{t,w}(G_g C_c^T).
@@ -159,6 +161,13 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
                         const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
                         int32_t group_size, float tau, float* scores_dev, float* probs_dev,
                         int32_t* argmax_dev, void* stream);
+
+/* softmax(scores / tau) and first argmax inside groups: group g covers
+ * scores[g * stride .. g * stride + group_size).  stride >= group_size lets a caller score
+ * prefixes of a wider candidate list (evaluate_asd.py:94-100 scores the first 2, 4, 6).
+ * probs_dev (nullable) is [n_groups, group_size] dense; argmax_dev (nullable) [n_groups]. */
+int jegal_group_softmax(jegal_ctx* ctx, const float* scores_dev, int32_t n_groups, int32_t group_size,
+                        int64_t stride, float tau, float* probs_dev, int32_t* argmax_dev, void* stream);
 
 #ifdef __cplusplus
 }

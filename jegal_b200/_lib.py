@@ -32,6 +32,7 @@ SYMBOLS = [
     "jegal_rank_of_positive",
     "jegal_spot",
     "jegal_simpool_pairs",
+    "jegal_group_softmax",
 ]
 
 F32, F16, BF16 = 0, 1, 2
@@ -89,7 +90,7 @@ def load() -> C.CDLL:
     lib.jegal_layout_rows.restype = i64
     lib.jegal_layout_clips.argtypes = [vp]
     lib.jegal_layout_clips.restype = i32
-    lib.jegal_prep.argtypes = [vp, vp, vp, C.c_int, C.c_int, f32, f32, C.c_int, vp, vp, vp]
+    lib.jegal_prep.argtypes = [vp, vp, vp, C.c_int, C.c_int, f32, f32, C.c_int, vp, vp, vp, vp]
     lib.jegal_simpool_allpairs.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, i64, i64, vp]
     lib.jegal_topk.argtypes = [vp, vp, i32, i32, i64, i32, i32, vp, vp, vp]
     lib.jegal_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
         lib.jegal_spot.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, f32, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp]
     if hasattr(lib, "jegal_simpool_pairs"):
         lib.jegal_simpool_pairs.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]
+    if hasattr(lib, "jegal_group_softmax"):
+        lib.jegal_group_softmax.argtypes = [vp, vp, i32, i32, i64, f32, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("jegal_layout_clips",):

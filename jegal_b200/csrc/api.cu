@@ -17,14 +17,14 @@ int set_err(jegal_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
-int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows,
-                      int op_dtype) {
+int make_box_tmap_impl(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows, int op_dtype,
+                       int box_rows) {
   auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ctx->encode_tiled);
   const CUtensorMapDataType dt =
       op_dtype == JEGAL_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kD), static_cast<cuuint64_t>(n_rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kD) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kTileRows)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(out, dt, 2, const_cast<void*>(rows_dev), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -32,6 +32,11 @@ int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, in
   if (r != CUDA_SUCCESS)
     return set_err(ctx, JEGAL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
   return JEGAL_OK;
+}
+
+int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows,
+                      int op_dtype) {
+  return make_box_tmap_impl(ctx, out, rows_dev, n_rows, op_dtype, kTileRows);
 }
 
 namespace {
@@ -222,12 +227,12 @@ int32_t jegal_layout_clips(const jegal_layout* L) { return L ? L->n_clips : 0; }
 
 int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype,
                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
-               float* inv_meannorm_dev, void* stream) {
+               float* inv_meannorm_dev, void* mean_rows_dev, void* stream) {
   if (!ctx || !layout || !emb_dev || !out_rows_dev) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
   if ((reinterpret_cast<uintptr_t>(emb_dev) | reinterpret_cast<uintptr_t>(out_rows_dev)) & 15u)
     return set_err(ctx, JEGAL_ERR_ARG, "prep: buffers must be 16-byte aligned");
   return launch_prep(ctx, layout, emb_dev, in_dtype, normalize_rows, row_eps, mean_eps, out_dtype,
-                     out_rows_dev, inv_meannorm_dev, static_cast<cudaStream_t>(stream));
+                     out_rows_dev, inv_meannorm_dev, mean_rows_dev, static_cast<cudaStream_t>(stream));
 }
 
 int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
@@ -256,8 +261,13 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
     case JEGAL_POOL_MAX_MAX: cols_are_gest = false; col_op = OP_MAX; row_op = OP_MAX; break;
     default: return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: bad pool_mode");
   }
-  const int force = env_int("JEGAL_SIMPOOL_COLS", -1);  // testing knob: 0 = content, 1 = gesture
-  if (force >= 0 && col_op == row_op) cols_are_gest = force != 0;
+  if (col_op == row_op) {
+    // either orientation is exact: put the longer clips on the column side (fewer, longer
+    // in-register reductions; fewer cross-lane combines per tile)
+    cols_are_gest = gest_layout->rows * static_cast<int64_t>(nC) >= cont_layout->rows * static_cast<int64_t>(nG);
+    const int force = env_int("JEGAL_SIMPOOL_COLS", -1);  // testing knob: 0 = content, 1 = gesture
+    if (force >= 0) cols_are_gest = force != 0;
+  }
 
   jegal_layout* LC = const_cast<jegal_layout*>(cols_are_gest ? gest_layout : cont_layout);
   const jegal_layout* LR = cols_are_gest ? cont_layout : gest_layout;

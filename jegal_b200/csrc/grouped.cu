@@ -1,0 +1,545 @@
+// K3 (word spotting) and K4 (listed clip pairs, e.g. active-speaker groups) for sm_100a.
+//
+// Both score LISTED (gesture clip, content clip) pairs instead of all pairs, so the
+// work per byte is tiny (T x W x 512 MACs for (T + W) x 1 KB of operands): these
+// kernels are HBM-bound and are built to stream, not to saturate the tensor pipe.
+//
+//   item = one pair; its T frames are the M side (TMEM lane = frame = one epilogue
+//   thread), its W <= 64 words the N side (columns), so everything the reference
+//   does "per frame over words" (softmax over words, evaluate_spotting.py:52-54;
+//   max over words) is register-local, and only per-frame scalars cross lanes.
+//
+//   warp 0  TMA producer: k-block ring (frames 32 rows per box so short clips do not
+//           drag 128 rows through L2; words 16 rows per box), runs ahead across items
+//   warp 1  tcgen05.mma issuer: M = 128, N = roundup16(W), 32 MMAs per row tile
+//   warp 2  TMEM allocator (4 accumulator buffers of 64 columns)
+//   warps 4-7 epilogue: tcgen05.ld -> softmax / pooling -> coalesced stores
+//
+// Items are dealt round-robin to a persistent grid of one CTA per SM.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace jegal {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kGThreads = 256;
+constexpr int kGStages = 8;
+constexpr int kNMax = 64;                        // words per clip on the N side
+constexpr uint32_t kGBytesG = 128 * 128;         // 128 frames x 64 elements x 2 B
+constexpr uint32_t kGBytesC = kNMax * 128;       // 64 words  x 64 elements x 2 B
+constexpr uint32_t kGStageBytes = kGBytesG + kGBytesC;
+constexpr int kNumAcc = 4;
+constexpr uint32_t kGTmemCols = kNumAcc * kNMax;  // 256
+constexpr int kBoxG = 32, kBoxC = 16;
+
+enum GroupedEpi : int { EPI_SPOT = 0, EPI_POOL = 1 };
+
+struct GroupedParams {
+  int32_t n_items;
+  const int32_t* item_g;  // nullable: item i -> gesture clip (default i)
+  const int32_t* item_c;  // nullable: item i -> content clip (default i)
+  const int32_t* cu_T;
+  const int32_t* cu_W;
+  uint32_t idesc_base;    // instruction descriptor with N = 0
+  // spotting
+  const int32_t* word_idx;
+  float inv_tau;
+  float* heat;
+  float* full_heat;
+  const int64_t* full_off;
+  int32_t* pred_frame;
+  float* pred_score;
+  const int32_t* win_lo;
+  const int32_t* win_hi;
+  float thresh;
+  uint8_t* correct;
+  // pooling
+  int32_t pool_mode;
+  const float* gscale;
+  const float* cscale;
+  float* scores;
+};
+
+struct Item {
+  int32_t g, c, g_row0, T, c_row0, W, n_rt, n16;
+};
+
+__device__ __forceinline__ Item load_item(const GroupedParams& p, int32_t i) {
+  Item it;
+  it.g = p.item_g ? __ldg(p.item_g + i) : i;
+  it.c = p.item_c ? __ldg(p.item_c + i) : i;
+  it.g_row0 = __ldg(p.cu_T + it.g);
+  it.T = __ldg(p.cu_T + it.g + 1) - it.g_row0;
+  it.c_row0 = __ldg(p.cu_W + it.c);
+  it.W = __ldg(p.cu_W + it.c + 1) - it.c_row0;
+  it.n_rt = (it.T + 127) >> 7;
+  it.n16 = (it.W + 15) >> 4;
+  return it;
+}
+
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int kEpi>
+__global__ void __launch_bounds__(kGThreads, 1)
+grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmC,
+               const GroupedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t bars = base + kGStages * kGStageBytes;
+  auto st_g = [&](int s) { return base + s * kGStageBytes; };
+  auto st_c = [&](int s) { return base + s * kGStageBytes + kGBytesG; };
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (kGStages + s); };
+  auto t_full = [&](int b) { return bars + 8u * (2 * kGStages + b); };
+  auto t_empty = [&](int b) { return bars + 8u * (2 * kGStages + kNumAcc + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kGStages + 2 * kNumAcc);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
+  // epilogue scratch (after the tmem slot): 4 warps x 64 floats + 4 x (float,int)
+  float* epi_f = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
+  int32_t* epi_i = reinterpret_cast<int32_t*>(epi_f + 4 * kNMax + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmG);
+    prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kGStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < kNumAcc; ++b) {
+      mbar_init(t_full(b), 1);
+      mbar_init(t_empty(b), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, kGTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t pol = policy_evict_first();  // every operand byte is used once
+      uint32_t s = 0, ph = 0;
+      for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
+        const Item it = load_item(p, i);
+        for (int32_t rt = 0; rt < it.n_rt; ++rt) {
+          const int32_t rows = min(128, it.T - rt * 128);
+          const int32_t nb = (rows + kBoxG - 1) / kBoxG;
+          const uint32_t bytes = nb * (kBoxG * 128) + it.n16 * (kBoxC * 128);
+          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+            mbar_wait(empty(s), ph ^ 1u);
+            mbar_arrive_expect_tx(full(s), bytes);
+            for (int32_t b = 0; b < nb; ++b)
+              tma_load_2d(&tmG, full(s), st_g(s) + b * (kBoxG * 128), kb * kBlockK,
+                          it.g_row0 + rt * 128 + b * kBoxG, pol);
+            for (int32_t b = 0; b < it.n16; ++b)
+              tma_load_2d(&tmC, full(s), st_c(s) + b * (kBoxC * 128), kb * kBlockK, it.c_row0 + b * kBoxC, pol);
+            if (++s == kGStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      uint32_t s = 0, ph = 0, tile = 0;
+      for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
+        const Item it = load_item(p, i);
+        const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(it.n16 * 16) >> 3) << 17;
+        for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
+          const uint32_t buf = tile % kNumAcc;
+          mbar_wait(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kNMax;
+          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+            mbar_wait(full(s), ph);
+            tc_fence_after();
+            const uint64_t dG = make_smem_desc_sw128(st_g(s));
+            const uint64_t dC = make_smem_desc_sw128(st_c(s));
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16<1>(d_tmem, dG + 2u * k, dC + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit<1>(empty(s));
+            if (++s == kGStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+          umma_commit<1>(t_full(buf));
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int et = q * 32 + lane;  // frame within the row tile
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t tile = 0;
+    for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
+      const Item it = load_item(p, i);
+      // per-item state
+      float best_v = -1.0f;
+      int32_t best_t = 0x7fffffff;
+      float racc = 0.f;                   // POOL: running reduction over frames
+      float wmax0 = -INFINITY, wmax1 = -INFINITY;  // POOL max_t_mean_w: running max of words lane, lane+32
+      int32_t target = 0;
+      float* fh = nullptr;
+      if constexpr (kEpi == EPI_SPOT) {
+        target = __ldg(p.word_idx + i);
+        if (p.full_heat) fh = p.full_heat + __ldg(p.full_off + i);
+      } else {
+        if (p.pool_mode == JEGAL_POOL_MAX_MAX) racc = -INFINITY;
+      }
+      for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
+        const uint32_t buf = tile % kNumAcc;
+        mbar_wait(t_full(buf), (tile / kNumAcc) & 1u);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + lane_off + buf * kNMax;
+        uint32_t v[kNMax];
+#pragma unroll
+        for (int g = 0; g < kNMax / 16; ++g) {
+          if (g < it.n16) {
+            uint32_t r[16];
+            tmem_ld_32x16(t_addr + g * 16, r);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[g * 16 + j] = r[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[g * 16 + j] = 0u;
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty(buf));
+
+        const int32_t t = rt * 128 + et;
+        const bool valid = t < it.T;
+        if constexpr (kEpi == EPI_SPOT) {
+          // softmax over words of s / tau (evaluate_spotting.py:52-54), per frame
+          float m = -INFINITY;
+#pragma unroll
+          for (int w = 0; w < kNMax; ++w)
+            if (w < it.W) m = fmaxf(m, __uint_as_float(v[w]));
+          float den = 0.f, pt = 0.f;
+#pragma unroll
+          for (int w = 0; w < kNMax; ++w) {
+            if (w < it.W) {
+              const float e = __expf((__uint_as_float(v[w]) - m) * p.inv_tau);
+              v[w] = __float_as_uint(e);
+              den += e;
+              if (w == target) pt = e;
+            }
+          }
+          const float inv_den = 1.0f / den;
+          pt *= inv_den;
+          if (valid) {
+            if (p.heat) p.heat[it.g_row0 + t] = pt;
+            if (fh) {
+#pragma unroll
+              for (int w = 0; w < kNMax; ++w)
+                if (w < it.W) fh[static_cast<int64_t>(w) * it.T + t] = __uint_as_float(v[w]) * inv_den;
+            }
+            if (pt > best_v) {  // frames arrive in increasing order: strict > keeps the first maximum
+              best_v = pt;
+              best_t = t;
+            }
+          }
+        } else {
+          if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
+            // max over frames first: per word, reduce across the warp's valid lanes
+#pragma unroll
+            for (int w = 0; w < kNMax; ++w) {
+              if (w < it.W) {
+                float x = valid ? __uint_as_float(v[w]) : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+                if (lane == (w & 31)) {
+                  if (w < 32) wmax0 = fmaxf(wmax0, x); else wmax1 = fmaxf(wmax1, x);
+                }
+              }
+            }
+          } else {
+            float c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? 0.f : -INFINITY;
+#pragma unroll
+            for (int w = 0; w < kNMax; ++w) {
+              if (w < it.W) {
+                const float x = __uint_as_float(v[w]);
+                c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? c + x : fmaxf(c, x);
+              }
+            }
+            if (valid) racc = p.pool_mode == JEGAL_POOL_MAX_MAX ? fmaxf(racc, c) : racc + c;
+          }
+        }
+      }
+      // ---- per-item finalisation across the 4 epilogue warps
+      if constexpr (kEpi == EPI_SPOT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+          const int32_t ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+          if (ov > best_v || (ov == best_v && ot < best_t)) {
+            best_v = ov;
+            best_t = ot;
+          }
+        }
+        if (lane == 0) {
+          epi_f[4 * kNMax + q] = best_v;
+          epi_i[q] = best_t;
+        }
+        bar_sync_epi();
+        if (q == 0 && lane == 0) {
+          float bv = epi_f[4 * kNMax];
+          int32_t bt = epi_i[0];
+          for (int w = 1; w < 4; ++w) {
+            const float ov = epi_f[4 * kNMax + w];
+            const int32_t ot = epi_i[w];
+            if (ov > bv || (ov == bv && ot < bt)) {
+              bv = ov;
+              bt = ot;
+            }
+          }
+          if (p.pred_frame) p.pred_frame[i] = bt;
+          if (p.pred_score) p.pred_score[i] = bv;
+          if (p.correct) {
+            const bool ok = bt >= __ldg(p.win_lo + i) && bt <= __ldg(p.win_hi + i) && bv >= p.thresh;
+            p.correct[i] = ok ? 1 : 0;
+          }
+        }
+        bar_sync_epi();
+      } else {
+        const float gs = p.gscale ? __ldg(p.gscale + it.g) : 1.0f;
+        const float cs = p.cscale ? __ldg(p.cscale + it.c) : 1.0f;
+        if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
+          epi_f[q * kNMax + lane] = wmax0;
+          epi_f[q * kNMax + 32 + lane] = wmax1;
+          bar_sync_epi();
+          if (q == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int w = h * 32 + lane;
+              if (w < it.W) {
+                float m = epi_f[w];
+#pragma unroll
+                for (int ww = 1; ww < 4; ++ww) m = fmaxf(m, epi_f[ww * kNMax + w]);
+                s += m;
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) p.scores[i] = s / static_cast<float>(it.W) * gs * cs;
+          }
+          bar_sync_epi();
+        } else {
+          const bool is_max = p.pool_mode == JEGAL_POOL_MAX_MAX;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, racc, o);
+            racc = is_max ? fmaxf(racc, ov) : racc + ov;
+          }
+          if (lane == 0) epi_f[4 * kNMax + q] = racc;
+          bar_sync_epi();
+          if (q == 0 && lane == 0) {
+            float r = epi_f[4 * kNMax];
+            for (int w = 1; w < 4; ++w) r = is_max ? fmaxf(r, epi_f[4 * kNMax + w]) : r + epi_f[4 * kNMax + w];
+            float sc = gs * cs;
+            if (p.pool_mode == JEGAL_POOL_MEAN_MEAN) sc /= static_cast<float>(it.T) * static_cast<float>(it.W);
+            if (p.pool_mode == JEGAL_POOL_MAX_W_MEAN_T) sc /= static_cast<float>(it.T);
+            p.scores[i] = r * sc;
+          }
+          bar_sync_epi();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, kGTmemCols);
+}
+
+constexpr size_t grouped_smem_bytes() {
+  return 1024 + static_cast<size_t>(kGStages) * kGStageBytes + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
+         sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4 + 16;
+}
+
+// one thread per group: softmax(scores / tau) within the group + first argmax
+// (evaluate_asd.py:47-51,99)
+__global__ void group_softmax_kernel(const float* __restrict__ scores, int32_t n_groups, int32_t gsz,
+                                     int64_t stride, float inv_tau, float* __restrict__ probs,
+                                     int32_t* __restrict__ argmax) {
+  const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const float* s = scores + static_cast<int64_t>(g) * stride;
+  float m = -INFINITY;
+  int32_t am = 0;
+  for (int32_t k = 0; k < gsz; ++k) {
+    const float x = __ldg(s + k);
+    if (x > m) {
+      m = x;
+      am = k;
+    }
+  }
+  if (argmax) argmax[g] = am;
+  if (probs) {
+    float den = 0.f;
+    for (int32_t k = 0; k < gsz; ++k) den += expf((__ldg(s + k) - m) * inv_tau);
+    const float inv = 1.0f / den;
+    for (int32_t k = 0; k < gsz; ++k)
+      probs[static_cast<int64_t>(g) * gsz + k] = expf((__ldg(s + k) - m) * inv_tau) * inv;
+  }
+}
+
+template <int kEpi>
+int launch_grouped(jegal_ctx* ctx, const CUtensorMap& tmG, const CUtensorMap& tmC, const GroupedParams& p,
+                   cudaStream_t stream) {
+  auto kern = grouped_kernel<kEpi>;
+  constexpr size_t smem = grouped_smem_bytes();
+  static bool configured = false;
+  if (!configured) {
+    JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  int grid = ctx->sm_count;
+  if (p.n_items < grid) grid = p.n_items;
+  kern<<<grid, kGThreads, smem, stream>>>(tmG, tmC, p);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // namespace
+
+}  // namespace jegal
+
+using namespace jegal;
+
+namespace {
+
+int check_w(jegal_ctx* ctx, const jegal_layout* cont, const char* who) {
+  if (cont->max_len > kNMax)
+    return set_err(ctx, JEGAL_ERR_UNSUPPORTED, std::string(who) + ": a content clip has " +
+                                                   std::to_string(cont->max_len) + " words; at most " +
+                                                   std::to_string(kNMax) + " are supported");
+  return JEGAL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
+               const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
+               const int32_t* word_idx_dev, float tau, float* heat_dev, float* full_heat_dev,
+               const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
+               const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh, uint8_t* correct_dev,
+               void* stream_) {
+  if (!ctx || !gest_layout || !cont_layout || !gest_rows_dev || !cont_rows_dev || !word_idx_dev)
+    return set_err(ctx, JEGAL_ERR_ARG, "spot: null argument");
+  if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16) return set_err(ctx, JEGAL_ERR_ARG, "spot: bad op_dtype");
+  if (gest_layout->n_clips != cont_layout->n_clips)
+    return set_err(ctx, JEGAL_ERR_ARG, "spot: gesture and content layouts must hold the same clips");
+  if (!(tau > 0.f)) return set_err(ctx, JEGAL_ERR_ARG, "spot: tau must be > 0");
+  if (full_heat_dev && !full_off_dev) return set_err(ctx, JEGAL_ERR_ARG, "spot: full_heat needs full_off");
+  if (correct_dev && (!win_lo_dev || !win_hi_dev)) return set_err(ctx, JEGAL_ERR_ARG, "spot: correct needs win_lo/win_hi");
+  if (gest_layout->n_clips == 0) return JEGAL_OK;
+  int rc = check_w(ctx, cont_layout, "spot");
+  if (rc != JEGAL_OK) return rc;
+  GroupedParams p{};
+  p.n_items = gest_layout->n_clips;
+  p.cu_T = gest_layout->cu_dev;
+  p.cu_W = cont_layout->cu_dev;
+  p.idesc_base = ptx::make_idesc_f16(op_dtype == JEGAL_BF16 ? 1u : 0u, 128, 0);
+  p.word_idx = word_idx_dev;
+  p.inv_tau = 1.0f / tau;
+  p.heat = heat_dev;
+  p.full_heat = full_heat_dev;
+  p.full_off = full_off_dev;
+  p.pred_frame = pred_frame_dev;
+  p.pred_score = pred_score_dev;
+  p.win_lo = win_lo_dev;
+  p.win_hi = win_hi_dev;
+  p.thresh = thresh;
+  p.correct = correct_dev;
+  CUtensorMap tmG, tmC;
+  rc = make_box_tmap_impl(ctx, &tmG, gest_rows_dev, gest_layout->rows, op_dtype, kBoxG);
+  if (rc != JEGAL_OK) return rc;
+  rc = make_box_tmap_impl(ctx, &tmC, cont_rows_dev, cont_layout->rows, op_dtype, kBoxC);
+  if (rc != JEGAL_OK) return rc;
+  return launch_grouped<EPI_SPOT>(ctx, tmG, tmC, p, static_cast<cudaStream_t>(stream_));
+}
+
+int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
+                        const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
+                        int pool_mode, const float* gscale_dev, const float* cscale_dev,
+                        const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
+                        int32_t group_size, float tau, float* scores_dev, float* probs_dev,
+                        int32_t* argmax_dev, void* stream_) {
+  if (!ctx || !gest_layout || !cont_layout || !gest_rows_dev || !cont_rows_dev || !scores_dev)
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: null argument");
+  if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: bad op_dtype");
+  if (pool_mode < 0 || pool_mode > 3) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: bad pool_mode");
+  if (n_pairs < 0) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: negative n_pairs");
+  if (!pair_gest_dev && n_pairs > gest_layout->n_clips) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: n_pairs exceeds clips");
+  if (!pair_cont_dev && n_pairs > cont_layout->n_clips) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: n_pairs exceeds clips");
+  const bool want_groups = probs_dev || argmax_dev;
+  if (want_groups && (group_size < 1 || n_pairs % group_size != 0 || !(tau > 0.f)))
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: group_size must divide n_pairs and tau must be > 0");
+  if (n_pairs == 0) return JEGAL_OK;
+  int rc = check_w(ctx, cont_layout, "simpool_pairs");
+  if (rc != JEGAL_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GroupedParams p{};
+  p.n_items = n_pairs;
+  p.item_g = pair_gest_dev;
+  p.item_c = pair_cont_dev;
+  p.cu_T = gest_layout->cu_dev;
+  p.cu_W = cont_layout->cu_dev;
+  p.idesc_base = ptx::make_idesc_f16(op_dtype == JEGAL_BF16 ? 1u : 0u, 128, 0);
+  p.pool_mode = pool_mode;
+  p.gscale = gscale_dev;
+  p.cscale = cscale_dev;
+  p.scores = scores_dev;
+  CUtensorMap tmG, tmC;
+  rc = make_box_tmap_impl(ctx, &tmG, gest_rows_dev, gest_layout->rows, op_dtype, kBoxG);
+  if (rc != JEGAL_OK) return rc;
+  rc = make_box_tmap_impl(ctx, &tmC, cont_rows_dev, cont_layout->rows, op_dtype, kBoxC);
+  if (rc != JEGAL_OK) return rc;
+  rc = launch_grouped<EPI_POOL>(ctx, tmG, tmC, p, stream);
+  if (rc != JEGAL_OK) return rc;
+  if (want_groups) {
+    const int32_t n_groups = n_pairs / group_size;
+    group_softmax_kernel<<<(n_groups + 127) / 128, 128, 0, stream>>>(scores_dev, n_groups, group_size, group_size,
+                                                                    1.0f / tau, probs_dev, argmax_dev);
+    JEGAL_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  return JEGAL_OK;
+}
+
+int jegal_group_softmax(jegal_ctx* ctx, const float* scores_dev, int32_t n_groups, int32_t group_size,
+                        int64_t stride, float tau, float* probs_dev, int32_t* argmax_dev, void* stream_) {
+  if (!ctx || !scores_dev) return set_err(ctx, JEGAL_ERR_ARG, "group_softmax: null argument");
+  if (n_groups < 0 || group_size < 1 || stride < group_size || !(tau > 0.f))
+    return set_err(ctx, JEGAL_ERR_ARG, "group_softmax: bad shape or tau");
+  if (n_groups == 0) return JEGAL_OK;
+  group_softmax_kernel<<<(n_groups + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+      scores_dev, n_groups, group_size, stride, 1.0f / tau, probs_dev, argmax_dev);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // extern "C"

@@ -95,7 +95,7 @@ int launch_row2clip(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int6
                     int32_t* row2clip_dev, cudaStream_t stream);
 int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int in_dtype,
                 int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows,
-                float* inv_meannorm, cudaStream_t stream);
+                float* inv_meannorm, void* mean_rows, cudaStream_t stream);
 int launch_topk(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
                 int32_t idx_offset, float* out_val, int32_t* out_idx, cudaStream_t stream);
 int launch_topk_merge(jegal_ctx* ctx, const float* vals, const int32_t* idxs, int32_t n_lists,
@@ -104,6 +104,9 @@ int launch_rank_of_positive(jegal_ctx* ctx, const float* scores, int32_t n_q, in
                             int64_t ld_row, int64_t ld_col, const int32_t* gt, int32_t* n_greater,
                             int32_t* n_equal, cudaStream_t stream);
 
+// tensor map over [n_rows, 512] 16-bit rows, box = 64 elements x box_rows rows, 128 B swizzle
+int make_box_tmap_impl(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows, int op_dtype,
+                       int box_rows);
 int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows,
                       int op_dtype);
 

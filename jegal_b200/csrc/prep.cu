@@ -66,11 +66,12 @@ template <int kInDtype, int kOutDtype>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 prep_kernel(const void* __restrict__ emb, const int32_t* __restrict__ cu, int32_t n_clips,
             int normalize_rows, float row_eps, float mean_eps, void* __restrict__ out,
-            float* __restrict__ inv_meannorm) {
+            float* __restrict__ inv_meannorm, void* __restrict__ mean_rows) {
   __shared__ float colsum[kPrepWarps][kD];
   __shared__ float red[kPrepWarps];
+  __shared__ float mean_s[kD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool want_mean = inv_meannorm != nullptr;
+  const bool want_mean = inv_meannorm != nullptr || mean_rows != nullptr;
   for (int32_t clip = blockIdx.x; clip < n_clips; clip += gridDim.x) {
     const int32_t r0 = __ldg(cu + clip), r1 = __ldg(cu + clip + 1);
     float cs[16];
@@ -115,6 +116,7 @@ prep_kernel(const void* __restrict__ emb, const int32_t* __restrict__ cu, int32_
         float m = s * inv_len;
         // numpy's .mean(axis=0) of an fp16 array returns fp16 (fp32 accumulate): mirror that rounding
         if constexpr (kInDtype == JEGAL_F16) m = __half2float(__float2half_rn(m));
+        mean_s[c] = m;
         part += m * m;
       }
       part = warp_sum(part);
@@ -124,7 +126,19 @@ prep_kernel(const void* __restrict__ emb, const int32_t* __restrict__ cu, int32_
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < kPrepWarps; ++w) tot += red[w];
-        inv_meannorm[clip] = 1.0f / fmaxf(sqrtf(tot), mean_eps);
+        const float inv = 1.0f / fmaxf(sqrtf(tot), mean_eps);
+        if (inv_meannorm) inv_meannorm[clip] = inv;
+        red[0] = inv;
+      }
+      __syncthreads();
+      if (mean_rows) {
+        const float inv = red[0];
+        if (threadIdx.x < kD / 8) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = mean_s[threadIdx.x * 8 + i] * inv;
+          store8<kOutDtype>(mean_rows, clip, threadIdx.x * 8, x);
+        }
       }
       __syncthreads();
     }
@@ -147,13 +161,13 @@ __global__ void row2clip_kernel(const int32_t* __restrict__ cu, int32_t n_clips,
 template <int kIn>
 int launch_prep_in(jegal_ctx* ctx, int out_dtype, dim3 grid, cudaStream_t stream, const void* emb,
                    const int32_t* cu, int32_t n_clips, int normalize_rows, float row_eps,
-                   float mean_eps, void* out, float* inv_meannorm) {
+                   float mean_eps, void* out, float* inv_meannorm, void* mean_rows) {
   if (out_dtype == JEGAL_BF16) {
     prep_kernel<kIn, JEGAL_BF16><<<grid, kPrepWarps * 32, 0, stream>>>(
-        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm);
+        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm, mean_rows);
   } else if (out_dtype == JEGAL_F16) {
     prep_kernel<kIn, JEGAL_F16><<<grid, kPrepWarps * 32, 0, stream>>>(
-        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm);
+        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm, mean_rows);
   } else {
     return set_err(ctx, JEGAL_ERR_ARG, "prep: out_dtype must be JEGAL_BF16 or JEGAL_F16");
   }
@@ -166,20 +180,20 @@ int launch_prep_in(jegal_ctx* ctx, int out_dtype, dim3 grid, cudaStream_t stream
 
 int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int in_dtype,
                 int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows,
-                float* inv_meannorm, cudaStream_t stream) {
+                float* inv_meannorm, void* mean_rows, cudaStream_t stream) {
   if (layout->n_clips == 0) return JEGAL_OK;
   const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 64;
   const dim3 grid(static_cast<unsigned>(layout->n_clips < cap ? layout->n_clips : cap));
   switch (in_dtype) {
     case JEGAL_F32:
       return launch_prep_in<JEGAL_F32>(ctx, out_dtype, grid, stream, emb, layout->cu_dev, layout->n_clips,
-                                       normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm);
+                                       normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm, mean_rows);
     case JEGAL_F16:
       return launch_prep_in<JEGAL_F16>(ctx, out_dtype, grid, stream, emb, layout->cu_dev, layout->n_clips,
-                                       normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm);
+                                       normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm, mean_rows);
     case JEGAL_BF16:
       return launch_prep_in<JEGAL_BF16>(ctx, out_dtype, grid, stream, emb, layout->cu_dev, layout->n_clips,
-                                        normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm);
+                                        normalize_rows, row_eps, mean_eps, out_rows, inv_meannorm, mean_rows);
     default:
       return set_err(ctx, JEGAL_ERR_ARG, "prep: bad in_dtype");
   }

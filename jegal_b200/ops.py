@@ -115,8 +115,10 @@ def prep(
     row_eps: float = 1e-12,
     mean_eps: float = 1e-12,
     out: Optional[torch.Tensor] = None,
-) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """K0: normalise + cast rows; optionally 1/||mean row|| per clip."""
+    want_mean_rows: bool = False,
+):
+    """K0: normalise + cast rows; optionally 1/||mean row|| per clip and the unit-norm
+    mean row of every clip.  Returns (rows16, inv_meannorm | None[, mean_rows16])."""
     _check_rows(emb, layout, "prep")
     if emb.dtype not in _DT or out_dtype not in (torch.bfloat16, torch.float16):
         raise JegalError("prep: unsupported dtype")
@@ -124,11 +126,14 @@ def prep(
     if out is None:
         out = torch.empty((layout.rows, 512), dtype=out_dtype, device=emb.device)
     scale = torch.empty((layout.n_clips,), dtype=torch.float32, device=emb.device) if want_mean_scale else None
+    mean_rows = torch.empty((layout.n_clips, 512), dtype=out_dtype, device=emb.device) if want_mean_rows else None
     rc = ctx.lib.jegal_prep(
         ctx.h, layout.h, _ptr(emb), _DT[emb.dtype], int(normalize), row_eps, mean_eps, _DT[out_dtype],
-        _ptr(out), _ptr(scale), _stream(),
+        _ptr(out), _ptr(scale), _ptr(mean_rows), _stream(),
     )
     ctx.check(rc, "jegal_prep")
+    if want_mean_rows:
+        return out, scale, mean_rows
     return out, scale
 
 
@@ -212,3 +217,115 @@ def rank_of_positive(
     )
     ctx.check(rc, "jegal_rank_of_positive")
     return ngt, neq
+
+
+def spot(
+    gest_rows: torch.Tensor,
+    gest_layout: Layout,
+    cont_rows: torch.Tensor,
+    cont_layout: Layout,
+    word_idx: torch.Tensor,
+    tau: float = 0.07,
+    want_heat: bool = True,
+    want_full: bool = False,
+    win_lo: Optional[torch.Tensor] = None,
+    win_hi: Optional[torch.Tensor] = None,
+    thresh: float = 0.5,
+) -> dict:
+    """K3: word spotting over n clips (clip i of both layouts).
+
+    Returns dict(heat [sum T] | None, full [sum T_i*W_i] | None, full_off int64 [n+1] | None,
+    pred_frame int32 [n], pred_score fp32 [n], correct uint8 [n] | None).
+    """
+    _check_rows(gest_rows, gest_layout, "spot gest")
+    _check_rows(cont_rows, cont_layout, "spot cont")
+    if gest_rows.dtype != cont_rows.dtype or gest_rows.dtype not in (torch.bfloat16, torch.float16):
+        raise JegalError("spot: operands must both be bf16 or both fp16 (outputs of prep)")
+    ctx = gest_layout.ctx
+    n = gest_layout.n_clips
+    dev = gest_rows.device
+    if word_idx.dtype != torch.int32 or word_idx.numel() != n or not word_idx.is_cuda:
+        raise JegalError("spot: word_idx must be CUDA int32 [n_clips]")
+    heat = torch.empty((gest_layout.rows,), dtype=torch.float32, device=dev) if want_heat else None
+    full = full_off = None
+    if want_full:
+        sizes = gest_layout.lengths.astype(np.int64) * cont_layout.lengths.astype(np.int64)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        full_off = torch.from_numpy(off).to(dev)
+        full = torch.empty((int(off[-1]),), dtype=torch.float32, device=dev)
+    pred_frame = torch.empty((n,), dtype=torch.int32, device=dev)
+    pred_score = torch.empty((n,), dtype=torch.float32, device=dev)
+    correct = None
+    if win_lo is not None:
+        if win_hi is None or win_lo.dtype != torch.int32 or win_hi.dtype != torch.int32:
+            raise JegalError("spot: win_lo/win_hi must both be int32")
+        correct = torch.empty((n,), dtype=torch.uint8, device=dev)
+    rc = ctx.lib.jegal_spot(
+        ctx.h, gest_layout.h, _ptr(gest_rows), cont_layout.h, _ptr(cont_rows), _DT[gest_rows.dtype],
+        _ptr(word_idx), float(tau), _ptr(heat), _ptr(full), _ptr(full_off), _ptr(pred_frame), _ptr(pred_score),
+        _ptr(win_lo), _ptr(win_hi), float(thresh), _ptr(correct), _stream(),
+    )
+    ctx.check(rc, "jegal_spot")
+    return dict(heat=heat, full=full, full_off=full_off, pred_frame=pred_frame, pred_score=pred_score, correct=correct)
+
+
+def simpool_pairs(
+    gest_rows: torch.Tensor,
+    gest_layout: Layout,
+    cont_rows: torch.Tensor,
+    cont_layout: Layout,
+    pair_gest: Optional[torch.Tensor],
+    pair_cont: Optional[torch.Tensor],
+    mode: str = "mean_mean",
+    gscale: Optional[torch.Tensor] = None,
+    cscale: Optional[torch.Tensor] = None,
+    group_size: int = 0,
+    tau: float = 0.07,
+    want_probs: bool = False,
+    n_pairs: Optional[int] = None,
+) -> dict:
+    """K4: pooled scores of listed (gesture clip, content clip) pairs, optional per-group
+    softmax(score / tau) and argmax (groups of `group_size` consecutive pairs)."""
+    _check_rows(gest_rows, gest_layout, "simpool_pairs gest")
+    _check_rows(cont_rows, cont_layout, "simpool_pairs cont")
+    if gest_rows.dtype != cont_rows.dtype or gest_rows.dtype not in (torch.bfloat16, torch.float16):
+        raise JegalError("simpool_pairs: operands must both be bf16 or both fp16 (outputs of prep)")
+    ctx = gest_layout.ctx
+    dev = gest_rows.device
+    for t in (pair_gest, pair_cont):
+        if t is not None and (t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous()):
+            raise JegalError("simpool_pairs: pair lists must be contiguous CUDA int32")
+    if n_pairs is None:
+        n_pairs = int(pair_gest.numel() if pair_gest is not None else pair_cont.numel() if pair_cont is not None
+                      else gest_layout.n_clips)
+    scores = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
+    probs = argmax = None
+    if group_size > 0:
+        argmax = torch.empty((n_pairs // group_size,), dtype=torch.int32, device=dev)
+        if want_probs:
+            probs = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
+    rc = ctx.lib.jegal_simpool_pairs(
+        ctx.h, gest_layout.h, _ptr(gest_rows), cont_layout.h, _ptr(cont_rows), _DT[gest_rows.dtype],
+        POOL_MODES[mode], _ptr(gscale), _ptr(cscale), _ptr(pair_gest), _ptr(pair_cont), n_pairs,
+        max(group_size, 1), float(tau), _ptr(scores), _ptr(probs), _ptr(argmax), _stream(),
+    )
+    ctx.check(rc, "jegal_simpool_pairs")
+    return dict(scores=scores, probs=probs, argmax=argmax)
+
+
+def group_softmax(scores: torch.Tensor, n_groups: int, group_size: int, stride: Optional[int] = None,
+                  tau: float = 0.07, want_probs: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    """softmax(scores / tau) + first argmax inside groups (group g = scores[g*stride : g*stride+group_size])."""
+    if not scores.is_cuda or scores.dtype != torch.float32 or not scores.is_contiguous():
+        raise JegalError("group_softmax: expected a contiguous CUDA fp32 tensor")
+    stride = group_size if stride is None else stride
+    if scores.numel() < (n_groups - 1) * stride + group_size:
+        raise JegalError("group_softmax: scores too short")
+    ctx = Context.get(scores.device.index)
+    probs = torch.empty((n_groups, group_size), dtype=torch.float32, device=scores.device) if want_probs else None
+    argmax = torch.empty((n_groups,), dtype=torch.int32, device=scores.device)
+    rc = ctx.lib.jegal_group_softmax(ctx.h, _ptr(scores), n_groups, group_size, stride, float(tau), _ptr(probs),
+                                     _ptr(argmax), _stream())
+    ctx.check(rc, "jegal_group_softmax")
+    return probs, argmax

@@ -176,7 +176,7 @@ def cfg5_gallery(n_query: int = 1000, n_gallery: int = 65536, T: int = 64, W: in
     dev = torch.device(device)
     gen = torch.Generator(device=device).manual_seed(seed)
     rng = np.random.default_rng(seed)
-    gt = rng.choice(n_gallery, size=n_query, replace=False).astype(np.int32)
+    gt = rng.choice(n_gallery, size=n_query, replace=n_query > n_gallery).astype(np.int32)
     gal = torch.randn((n_gallery * W, D), generator=gen, device=dev)
     q = 1.0 * torch.randn((n_query * T, D), generator=gen, device=dev)
     # frames of query q echo the words of its match: frame t speaks word t * W // T

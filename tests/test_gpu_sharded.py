@@ -1,0 +1,52 @@
+"""Gallery-sharded retrieval on >= 2 real GPUs (NCCL): N-GPU result == 1-GPU result, bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from jegal_b200 import ops, sharded, synth
+        Q, G, T, W, k = 64, 4099, 64, 16, 10  # gallery size not divisible by the world size
+        q, g, gt = synth.cfg5_gallery(Q, G, T, W, seed=5, device=dev)
+        ql = ops.Layout.from_lengths([T] * Q)
+        q_in = q.clone() if rank == 0 else torch.zeros_like(q)
+        q_in = sharded.broadcast_queries(q_in, Q * T, q.dtype, dev)
+        assert torch.equal(q_in, q)
+        q16, _ = ops.prep(q_in, ql)
+        lo, hi = sharded.shard_range(G, rank, world)
+        sl = ops.Layout.from_lengths([W] * (hi - lo))
+        s16, _ = ops.prep(g[lo * W:hi * W].contiguous(), sl)
+        v, i = sharded.retrieve_topk_sharded(q16, ql, s16, sl, lo, k=k)
+        gl = ops.Layout.from_lengths([W] * G)
+        g16, _ = ops.prep(g, gl)
+        rv, ri = ops.topk(ops.simpool_allpairs(q16, ql, g16, gl, "max_t_mean_w"), k)
+        assert torch.equal(i, ri) and torch.equal(v, rv)
+        assert np.array_equal(i[:, 0].cpu().numpy(), gt)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))

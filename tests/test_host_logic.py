@@ -1,0 +1,116 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/jegal_b200.h
+declares, the host logic of the scoring mirror, the synthetic generators, and that the
+product refuses to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from jegal_b200 import _lib, scoring, sharded, synth
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "jegal_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jegal_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/jegal_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names
+    assert b"sm_100a" in lib.jegal_version()
+
+
+def test_library_is_sm100a_only():
+    """The shipped .so carries sm_100a SASS with tcgen05 / TMA / TMEM instructions."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    g = [np.zeros((3, 512), np.float16)]
+    with pytest.raises(_lib.JegalError):
+        scoring.score_allpairs(g, g, "mean_mean")
+    with pytest.raises(_lib.JegalError):
+        scoring.compute_metrics(np.eye(4, dtype=np.float32))
+    with pytest.raises(_lib.JegalError):
+        scoring.get_similarity_cos(np.ones((1, 512), np.float32), np.ones((2, 512), np.float32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "jegal_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+    assert "oracle" not in open(os.path.join(ROOT, "jegal_b200", "scoring.py")).read().replace("the oracle", "")
+
+
+def test_metrics_from_counts_matches_reference_semantics():
+    rng = np.random.default_rng(3)
+    for x in (rng.standard_normal((50, 50)).astype(np.float32), rng.integers(0, 4, (30, 30)).astype(np.float32)):
+        ng, ne = oracle.rank_counts(x)
+        assert scoring._metrics_from_counts(ng, ne) == oracle.compute_metrics(x)
+
+
+def test_shard_ranges_cover_gallery():
+    for n, w in [(65536, 8), (10, 4), (3, 8), (0, 2), (1000, 3)]:
+        prev = 0
+        for r in range(w):
+            lo, hi = sharded.shard_range(n, r, w)
+            assert lo == prev and lo <= hi <= n
+            prev = hi
+        assert prev == n
+
+
+def test_synth_shapes_and_norms():
+    cs = synth.cfg1_samples()
+    assert [len(g) for g in cs.gesture_list()] == [56, 68] and [len(c) for c in cs.content_list()] == [8, 7]
+    n = np.linalg.norm(cs.gest.float().numpy(), axis=1)
+    assert np.abs(n - 1).max() < 2e-3 and cs.gest.dtype == torch.float16
+    cs = synth.cfg2_retrieval(n=50)
+    lt, lw = np.diff(cs.cu_t), np.diff(cs.cu_w)
+    assert lt.min() >= 25 and lt.max() <= 200 and lw.min() >= 4 and lw.max() <= 40
+    for i in range(cs.n):
+        for (_, s, e) in cs.boundaries[i]:
+            assert 0 <= s <= e < lt[i]
+    cs = synth.cfg3_spotting(n=40)
+    assert (np.diff(cs.cu_t) >= 25).all() and (np.diff(cs.cu_t) <= 220).all() and (np.diff(cs.cu_w) <= 12).all()
+    ds = synth.cfg4_asd(n_groups=5, tracks=4)
+    assert ds.pair_gest.tolist() == list(range(20)) and ds.pair_cont[:8].tolist() == [0, 0, 0, 0, 4, 4, 4, 4]
+    q, g, gt = synth.cfg5_gallery(4, 64, 8, 4)
+    assert q.shape == (32, 512) and g.shape == (256, 512) and len(gt) == 4
+
+
+def test_synth_structure_is_learnable():
+    """Diagonal pairs win and heatmaps peak inside the target word: the synthetic data exercises
+    real decisions (not degenerate ties)."""
+    cs = synth.make_clipset([60] * 12, [8] * 12, seed=9, with_targets=True)
+    s = oracle.simpool_allpairs(cs.gesture_list(), cs.content_list(), "max_t_mean_w")
+    assert (s.argmax(1) == np.arange(12)).mean() > 0.9
+    hit = 0
+    for i in range(cs.n):
+        a = oracle.get_attn_matrix(cs.gesture(i).numpy(), cs.content(i).numpy())
+        w = int(cs.target_word[i])
+        _, s0, e0 = cs.boundaries[i][w]
+        hit += oracle.spot_decision(a, w, s0, e0)[2]
+    assert hit >= 8
