@@ -92,7 +92,7 @@ class PackedClips:
             buf = torch.empty((total, 512), dtype=torch.float16 if dt == np.float16 else torch.float32,
                               pin_memory=pin and total > 0)
             if total:
-                np.concatenate(arrs, axis=0, out=buf.numpy(), dtype=dt, casting="same_kind")
+                np.concatenate(arrs, axis=0, out=buf.numpy(), casting="same_kind")
         else:
             buf = torch.from_numpy(np.ascontiguousarray(host))
             if pin and total > 0:
