@@ -276,13 +276,17 @@ def main_ours(args, wl, rank, local_rank, world):
             vv, ii = ops.topk_merge(vals.view(world, Q, k), idxs.view(world, Q, k))
         return vv.cpu(), ii.cpu()  # device->host read of the step's result (synchronises)
 
-    e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hv, hi_ = e2e_step()
-    sync_all()
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    if args.no_e2e:
+        e2e_steps = 0
+        e2e_dt = float("nan")
+    else:
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hv, hi_ = e2e_step()
+        sync_all()
+        e2e_dt = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     hb = torch.tensor([h2d], dtype=torch.int64, device=dev)
     if world > 1:
@@ -341,6 +345,7 @@ def main():
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", 0))

@@ -175,12 +175,13 @@ int jegal_layout_create(jegal_ctx* ctx, const int32_t* cu_len_host, int32_t n_cl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (cu_len_host[0] != 0) return set_err(ctx, JEGAL_ERR_ARG, "layout_create: cu_len[0] must be 0");
   bool aligned = true;
-  int32_t max_len = 0;
+  int32_t max_len = 0, min_len = 0x7fffffff;
   for (int32_t i = 0; i < n_clips; ++i) {
     const int32_t b = cu_len_host[i], e = cu_len_host[i + 1];
     if (e <= b)
       return set_err(ctx, JEGAL_ERR_ARG, "layout_create: clip " + std::to_string(i) + " is empty or offsets decrease");
     max_len = std::max(max_len, e - b);
+    min_len = std::min(min_len, e - b);
     if ((b >> 5) != ((e - 1) >> 5)) aligned = false;
   }
   auto* L = new (std::nothrow) jegal_layout();
@@ -190,17 +191,18 @@ int jegal_layout_create(jegal_ctx* ctx, const int32_t* cu_len_host, int32_t n_cl
   L->rows = cu_len_host[n_clips];
   L->max_len = max_len;
   L->warp_aligned = aligned;
+  L->uniform_len = (n_clips > 0 && min_len == max_len) ? max_len : 0;
   L->cu_host.assign(cu_len_host, cu_len_host + n_clips + 1);
   cudaError_t e = cudaSetDevice(ctx->device);
   if (e == cudaSuccess) e = cudaMalloc(&L->cu_dev, sizeof(int32_t) * (n_clips + 1));
-  if (e == cudaSuccess) e = cudaMalloc(&L->row2clip_dev, sizeof(int32_t) * std::max<int64_t>(L->rows, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&L->rowinfo_dev, sizeof(int4) * std::max<int64_t>(L->rows, 1));
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(L->cu_dev, L->cu_host.data(), sizeof(int32_t) * (n_clips + 1), cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) {
     jegal_layout_destroy(L);
     return set_err(ctx, JEGAL_ERR_CUDA, std::string("layout_create: ") + cudaGetErrorString(e));
   }
-  int rc = launch_row2clip(ctx, L->cu_dev, n_clips, L->rows, L->row2clip_dev, stream);
+  int rc = launch_rowinfo(ctx, L->cu_dev, n_clips, L->rows, L->rowinfo_dev, stream);
   if (rc == JEGAL_OK && cudaStreamSynchronize(stream) != cudaSuccess)  // one-time: layout is usable on any stream
     rc = set_err(ctx, JEGAL_ERR_CUDA, "layout_create: synchronize failed");
   if (rc != JEGAL_OK) {
@@ -214,7 +216,7 @@ int jegal_layout_create(jegal_ctx* ctx, const int32_t* cu_len_host, int32_t n_cl
 void jegal_layout_destroy(jegal_layout* L) {
   if (!L) return;
   if (L->cu_dev) cudaFree(L->cu_dev);
-  if (L->row2clip_dev) cudaFree(L->row2clip_dev);
+  if (L->rowinfo_dev) cudaFree(L->rowinfo_dev);
   for (auto* s : L->ctile_sets) {
     if (s->dev) cudaFree(s->dev);
     delete s;
@@ -290,7 +292,8 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   const int64_t chunk_bytes = static_cast<int64_t>(env_int("JEGAL_CHUNK_MB", 24)) << 20;
   p.chunk_rtiles = static_cast<int32_t>(std::max<int64_t>(1, chunk_bytes / (static_cast<int64_t>(width) * kD * 2)));
   p.n_rows_R = static_cast<int32_t>(LR->rows);
-  p.row2clip_R = LR->row2clip_dev;
+  p.rowinfo_R = LR->rowinfo_dev;
+  p.uni_len_R = LR->uniform_len;
   p.cu_R = LR->cu_dev;
   p.cu_C = LC->cu_dev;
   p.rscale = cols_are_gest ? cscale_dev : gscale_dev;

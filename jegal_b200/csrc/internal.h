@@ -33,7 +33,8 @@ struct SimpoolParams {
   int32_t n_rtiles;      // row tiles of (128 * cta_group) rows
   int32_t chunk_rtiles;  // row tiles per L2-resident phase
   int32_t n_rows_R;
-  const int32_t* row2clip_R;
+  int32_t uni_len_R;        // > 0: every row-side clip has this many rows (no per-row lookup)
+  const int4* rowinfo_R;    // per row {clip, clip's first row, clip's end row, 0}
   const int32_t* cu_R;
   const int32_t* cu_C;
   const float* rscale;  // nullable
@@ -64,7 +65,8 @@ struct jegal_layout {
   bool warp_aligned = false;  // every clip lies inside one aligned 32-row window
   std::vector<int32_t> cu_host;
   int32_t* cu_dev = nullptr;
-  int32_t* row2clip_dev = nullptr;
+  int4* rowinfo_dev = nullptr;  // per row {clip, first row, end row, 0}
+  int32_t uniform_len = 0;      // > 0 when all clips have the same length
   struct CTileSet {
     int width = 0;
     bool allow_split = false;
@@ -91,8 +93,8 @@ int set_err(jegal_ctx* ctx, int code, const std::string& msg);
 int launch_simpool(jegal_ctx* ctx, int cta_group, int col_op, int row_op, const CUtensorMap& tmR,
                    const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream);
 int launch_fill_f32(jegal_ctx* ctx, float* dst, int64_t n, float value, cudaStream_t stream);
-int launch_row2clip(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
-                    int32_t* row2clip_dev, cudaStream_t stream);
+int launch_rowinfo(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
+                   int4* rowinfo_dev, cudaStream_t stream);
 int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int in_dtype,
                 int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows,
                 float* inv_meannorm, void* mean_rows, cudaStream_t stream);

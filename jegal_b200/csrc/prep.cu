@@ -145,8 +145,8 @@ prep_kernel(const void* __restrict__ emb, const int32_t* __restrict__ cu, int32_
   }
 }
 
-__global__ void row2clip_kernel(const int32_t* __restrict__ cu, int32_t n_clips, int64_t rows,
-                                int32_t* __restrict__ row2clip) {
+__global__ void rowinfo_kernel(const int32_t* __restrict__ cu, int32_t n_clips, int64_t rows,
+                               int4* __restrict__ rowinfo) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += stride) {
     int32_t lo = 0, hi = n_clips;  // invariant: cu[lo] <= r < cu[hi]
@@ -154,7 +154,7 @@ __global__ void row2clip_kernel(const int32_t* __restrict__ cu, int32_t n_clips,
       const int32_t mid = (lo + hi) >> 1;
       if (__ldg(cu + mid) <= r) lo = mid; else hi = mid;
     }
-    row2clip[r] = lo;
+    rowinfo[r] = make_int4(lo, __ldg(cu + lo), __ldg(cu + lo + 1), 0);
   }
 }
 
@@ -199,14 +199,14 @@ int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int
   }
 }
 
-int launch_row2clip(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
-                    int32_t* row2clip_dev, cudaStream_t stream) {
+int launch_rowinfo(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
+                   int4* rowinfo_dev, cudaStream_t stream) {
   if (rows <= 0) return JEGAL_OK;
   const int threads = 256;
   int64_t blocks = (rows + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 32;
   if (blocks > cap) blocks = cap;
-  row2clip_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(cu_dev, n_clips, rows, row2clip_dev);
+  rowinfo_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(cu_dev, n_clips, rows, rowinfo_dev);
   JEGAL_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;
   return JEGAL_OK;

@@ -67,8 +67,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Arrive on a barrier addressed in the shared::cluster window (own or peer CTA).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
-               : "memory");
+  // default semantics (.release at .cta scope): the only thing ordered before this arrive is the
+  // tcgen05.ld of the accumulator (tcgen05.wait::ld + fence::before_thread_sync); a cluster-scope
+  // release would drain every outstanding global store first (ERRBAR, 16 % of the epilogue)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;

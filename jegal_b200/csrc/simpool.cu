@@ -18,9 +18,11 @@
 //     (16 KB per k-block), so every MMA reads A and B from smem and L2->smem
 //     traffic per MMA tile is halved with respect to streaming both operands;
 //   - warp 0: TMA producer, warp 1: tcgen05.mma issuer, warp 2: TMEM allocator,
-//     warps 4-7: epilogue (tcgen05.ld -> pooling -> global);
+//     warps 4-7 / 8-11: two epilogue warpgroups (tcgen05.ld -> pooling -> global), one
+//     per TMEM accumulator buffer, so every SM sub-partition has two epilogue warps
+//     whose TMEM-load / shuffle latencies interleave;
 //   - two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs
-//     of tile i+1; stationary-tile k-blocks are released one by one during the
+//     of tiles i+1 and i+2; stationary-tile k-blocks are released one by one during the
 //     last row tile of a unit so the next column tile's load overlaps too;
 //   - work is split over clusters by "row-tile steps" inside L2-sized phases of
 //     R so that all CTAs stream the same slice of R at the same time.
@@ -36,8 +38,9 @@ using namespace ptx;
 namespace {
 
 constexpr uint32_t kTileBytes = kTileRows * kBlockK * 2;  // 16384
-constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiGroups = 2;  // one epilogue warpgroup per TMEM accumulator buffer
+constexpr int kThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);  // 384
 
 template <int kOp>
 __device__ __forceinline__ float op_ident() {
@@ -123,6 +126,46 @@ __device__ __forceinline__ void emit(float acc, int32_t cclip, bool col_partial,
       atomic_max_f32(dst, val);
     } else {
       atomicAdd(dst, val);
+    }
+  }
+}
+
+// Pool one 32-column chunk of this thread's row: `em` marks the columns that end a segment.
+template <int kColOp, int kRowOp>
+__device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em, float& acc, int32_t& cclip,
+                                           bool col_partial, const RowCtx& rc, const SimpoolParams& p) {
+  if ((em & 0x7f7f7f7fu) == 0u) {
+    // fast path: segment ends (if any) only at columns 7/15/23/31 of the chunk
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
+      if ((em >> (8 * j + 7)) & 1u) {
+        emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+        ++cclip;
+        acc = op_ident<kColOp>();
+      }
+    }
+  } else {
+    // general path: one masked reduction per run of columns between segment ends
+    uint32_t rem = em;
+    uint32_t start = 0;
+    while (true) {
+      const uint32_t e = rem ? static_cast<uint32_t>(__ffs(rem) - 1) : 31u;
+      const uint32_t m = (e == 31u ? 0xffffffffu : ((1u << (e + 1)) - 1u)) & ~((1u << start) - 1u);
+      float r = op_ident<kColOp>();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = ((m >> j) & 1u) ? __uint_as_float(v[j]) : op_ident<kColOp>();
+        r = op_apply<kColOp>(r, x);
+      }
+      acc = op_apply<kColOp>(acc, r);
+      if (!rem) break;
+      emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+      ++cclip;
+      acc = op_ident<kColOp>();
+      rem &= rem - 1u;
+      start = e + 1u;
+      if (start >= 32u) break;
     }
   }
 }
@@ -281,7 +324,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue
-    const int q = warp - kEpiWarp0;  // TMEM lane quarter == warp % 4
+    const int q = (warp - kEpiWarp0) & 3;          // TMEM lane quarter == warp % 4
+    const uint32_t grp = (warp - kEpiWarp0) >> 2;  // this warpgroup drains accumulator buffer `grp`
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     UnitIter it(p, cluster, nclusters);
     int32_t ct, rt0, nrt;
@@ -294,15 +338,24 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       const uint32_t my_em = lane < 8 ? __ldg(&ctile->endmask[lane]) : 0u;
       const int nchunks = (n_valid + 31) >> 5;
       for (int32_t t = 0; t < nrt; ++t, ++tile) {
-        // per-row context for this tile (loads overlap the wait for the accumulator)
+        if ((tile & 1u) != grp) continue;  // the other warpgroup owns this tile
+        // per-row context for this tile (the load overlaps the wait for the accumulator)
         RowCtx rc;
         {
           const int32_t row = (rt0 + t) * UMMA_M + static_cast<int32_t>(rank) * kTileRows + q * 32 + lane;
-          rc.rclip = row < p.n_rows_R ? __ldg(p.row2clip_R + row) : -1;
           int32_t sb = 0, se = 1;
-          if (rc.rclip >= 0) {
-            sb = __ldg(p.cu_R + rc.rclip);
-            se = __ldg(p.cu_R + rc.rclip + 1);
+          rc.rclip = -1;
+          if (row < p.n_rows_R) {
+            if (p.uni_len_R > 0) {  // all row clips have the same length: no lookup at all
+              rc.rclip = row / p.uni_len_R;
+              sb = rc.rclip * p.uni_len_R;
+              se = sb + p.uni_len_R;
+            } else {
+              const int4 ri = __ldg(p.rowinfo_R + row);  // {clip, first row, end row, -}
+              rc.rclip = ri.x;
+              sb = ri.y;
+              se = ri.z;
+            }
           }
           float rs_ = (rc.rclip >= 0 && p.rscale) ? __ldg(p.rscale + rc.rclip) : 1.0f;
           if constexpr (kRowOp == OP_SUM) rs_ *= 1.0f / static_cast<float>(se - sb);
@@ -318,63 +371,40 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           const int32_t wrow0 = row - lane;
           rc.complete = sb >= wrow0 && se <= wrow0 + 32;
         }
-        const uint32_t buf = tile & 1u;
+        const uint32_t buf = grp;
         mbar_wait(t_full(buf), (tile >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_off + buf * UMMA_N;
 
-        float acc = op_ident<kColOp>();
-        int32_t cclip = clip0;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + ch * 32, v);
-          tmem_ld_wait();
-          if (ch == nchunks - 1) {
-            // accumulator fully read: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (kCG == 2) {
-                mbar_arrive_cluster(t_empty(buf) & kPeerBitMask);
-              } else {
-                mbar_arrive(t_empty(buf));
-              }
+        // hand the TMEM buffer back to the MMA warp once its last chunk sits in registers
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCG == 2) {
+              mbar_arrive_cluster(t_empty(buf) & kPeerBitMask);
+            } else {
+              mbar_arrive(t_empty(buf));
             }
           }
-          const uint32_t em = __shfl_sync(0xffffffffu, my_em, ch);
-          if ((em & 0x7f7f7f7fu) == 0u) {
-            // fast path: segment ends (if any) only at columns 7/15/23/31 of the chunk
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
-              if ((em >> (8 * j + 7)) & 1u) {
-                emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
-                ++cclip;
-                acc = op_ident<kColOp>();
-              }
-            }
-          } else {
-            // general path: one masked reduction per run of columns between segment ends
-            uint32_t rem = em;
-            uint32_t start = 0;
-            while (true) {
-              const uint32_t e = rem ? static_cast<uint32_t>(__ffs(rem) - 1) : 31u;
-              const uint32_t m = (e == 31u ? 0xffffffffu : ((1u << (e + 1)) - 1u)) & ~((1u << start) - 1u);
-              float r = op_ident<kColOp>();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float x = ((m >> j) & 1u) ? __uint_as_float(v[j]) : op_ident<kColOp>();
-                r = op_apply<kColOp>(r, x);
-              }
-              acc = op_apply<kColOp>(acc, r);
-              if (!rem) break;
-              emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
-              ++cclip;
-              acc = op_ident<kColOp>();
-              rem &= rem - 1u;
-              start = e + 1u;
-              if (start >= 32u) break;
-            }
+        };
+
+        float acc = op_ident<kColOp>();
+        int32_t cclip = clip0;
+        uint32_t va[32], vb[32];  // two chunks in flight: load c+1 while chunk c is pooled
+        tmem_ld_32x32(t_addr, va);
+        for (int ch = 0; ch < nchunks; ch += 2) {
+          const uint32_t em_a = __shfl_sync(0xffffffffu, my_em, ch);
+          const uint32_t em_b = __shfl_sync(0xffffffffu, my_em, ch + 1);
+          tmem_ld_wait();
+          if (ch + 1 < nchunks) tmem_ld_32x32(t_addr + (ch + 1) * 32, vb);
+          else release();
+          pool_chunk<kColOp, kRowOp>(va, em_a, acc, cclip, col_partial, rc, p);
+          if (ch + 1 < nchunks) {
+            tmem_ld_wait();
+            if (ch + 2 < nchunks) tmem_ld_32x32(t_addr + (ch + 2) * 32, va);
+            else release();
+            pool_chunk<kColOp, kRowOp>(vb, em_b, acc, cclip, col_partial, rc, p);
           }
         }
       }
@@ -397,7 +427,7 @@ constexpr size_t simpool_smem_bytes() {
          8 * (2 * kStages + 2 * kNumKBlocks + 4) + 16;
 }
 
-constexpr int kStagesDefault = 5;
+constexpr int kStagesDefault = 6;
 
 template <int kCG, int kColOp, int kRowOp>
 int launch_simpool_t(jegal_ctx* ctx, const CUtensorMap& tmR, const CUtensorMap& tmC,
