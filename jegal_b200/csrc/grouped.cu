@@ -98,9 +98,11 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   auto t_empty = [&](int b) { return bars + 8u * (2 * kGStages + kNumAcc + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * kGStages + 2 * kNumAcc);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
-  // epilogue scratch (after the tmem slot): 4 warps x 64 floats + 4 x (float,int)
-  float* epi_f = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
-  int32_t* epi_i = reinterpret_cast<int32_t*>(epi_f + 4 * kNMax + 4);
+  // epilogue scratch (after the tmem slot), double-buffered by item parity so one named barrier
+  // per item suffices: per parity 4 warps x 64 floats + 4 floats + 4 ints
+  constexpr int kScratchF = 4 * kNMax + 4;
+  float* epi_f0 = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
+  int32_t* epi_i0 = reinterpret_cast<int32_t*>(epi_f0 + 2 * kScratchF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,8 +132,11 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     if (elect_one()) {
       const uint64_t pol = policy_evict_first();  // every operand byte is used once
       uint32_t s = 0, ph = 0;
+      Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
       for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
-        const Item it = load_item(p, i);
+        const Item it = nxt;
+        // descriptor of the next item: its loads fly while this item's TMA is issued
+        nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
         for (int32_t rt = 0; rt < it.n_rt; ++rt) {
           const int32_t rows = min(128, it.T - rt * 128);
           const int32_t nb = (rows + kBoxG - 1) / kBoxG;
@@ -155,8 +160,10 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   } else if (warp == 1) {
     if (elect_one()) {
       uint32_t s = 0, ph = 0, tile = 0;
+      Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
       for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
-        const Item it = load_item(p, i);
+        const Item it = nxt;
+        nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
         const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(it.n16 * 16) >> 3) << 17;
         for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
           const uint32_t buf = tile % kNumAcc;
@@ -185,21 +192,32 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     const int q = warp - 4;
     const int et = q * 32 + lane;  // frame within the row tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t tile = 0;
-    for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
-      const Item it = load_item(p, i);
-      // per-item state
+    uint32_t tile = 0, parity = 0;
+    Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
+    for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x, parity ^= 1u) {
+      const Item it = nxt;
+      nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
+      float* epi_f = epi_f0 + parity * kScratchF;
+      int32_t* epi_i = epi_i0 + parity * 4;
+      // per-item state; every scalar the finalisation needs is fetched now, not after the barrier
       float best_v = -1.0f;
       int32_t best_t = 0x7fffffff;
       float racc = 0.f;                   // POOL: running reduction over frames
       float wmax0 = -INFINITY, wmax1 = -INFINITY;  // POOL max_t_mean_w: running max of words lane, lane+32
-      int32_t target = 0;
+      int32_t target = 0, wlo = 0, whi = 0;
+      float gs = 1.0f, cs = 1.0f;
       float* fh = nullptr;
       if constexpr (kEpi == EPI_SPOT) {
         target = __ldg(p.word_idx + i);
         if (p.full_heat) fh = p.full_heat + __ldg(p.full_off + i);
+        if (p.correct) {
+          wlo = __ldg(p.win_lo + i);
+          whi = __ldg(p.win_hi + i);
+        }
       } else {
         if (p.pool_mode == JEGAL_POOL_MAX_MAX) racc = -INFINITY;
+        if (p.gscale) gs = __ldg(p.gscale + it.g);
+        if (p.cscale) cs = __ldg(p.cscale + it.c);
       }
       for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
         const uint32_t buf = tile % kNumAcc;
@@ -313,14 +331,11 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           if (p.pred_frame) p.pred_frame[i] = bt;
           if (p.pred_score) p.pred_score[i] = bv;
           if (p.correct) {
-            const bool ok = bt >= __ldg(p.win_lo + i) && bt <= __ldg(p.win_hi + i) && bv >= p.thresh;
+            const bool ok = bt >= wlo && bt <= whi && bv >= p.thresh;
             p.correct[i] = ok ? 1 : 0;
           }
         }
-        bar_sync_epi();
       } else {
-        const float gs = p.gscale ? __ldg(p.gscale + it.g) : 1.0f;
-        const float cs = p.cscale ? __ldg(p.cscale + it.c) : 1.0f;
         if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
           epi_f[q * kNMax + lane] = wmax0;
           epi_f[q * kNMax + 32 + lane] = wmax1;
@@ -341,7 +356,6 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) p.scores[i] = s / static_cast<float>(it.W) * gs * cs;
           }
-          bar_sync_epi();
         } else {
           const bool is_max = p.pool_mode == JEGAL_POOL_MAX_MAX;
 #pragma unroll
@@ -359,7 +373,6 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
             if (p.pool_mode == JEGAL_POOL_MAX_W_MEAN_T) sc /= static_cast<float>(it.T);
             p.scores[i] = r * sc;
           }
-          bar_sync_epi();
         }
       }
     }
@@ -372,7 +385,7 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 
 constexpr size_t grouped_smem_bytes() {
   return 1024 + static_cast<size_t>(kGStages) * kGStageBytes + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
-         sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4 + 16;
+         2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + 16;
 }
 
 // one thread per group: softmax(scores / tau) within the group + first argmax

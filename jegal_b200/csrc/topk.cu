@@ -10,7 +10,7 @@
 namespace jegal {
 namespace {
 
-constexpr int kTopkWarps = 8;
+constexpr int kTopkWarps = 4;
 
 __device__ __forceinline__ bool better(float av, int32_t ai, float bv, int32_t bi) {
   return av > bv || (av == bv && ai < bi);
@@ -75,16 +75,45 @@ topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
   const int32_t n4 = vec_ok ? (n_g >> 2) : 0;
   const float4* row4 = reinterpret_cast<const float4*>(row);
-  for (int32_t base = warp * 32; base < n4; base += kTopkWarps * 32) {
-    const int32_t j4 = base + lane;
-    const bool valid = j4 < n4;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) x = __ldg(row4 + j4);
-    const int32_t j = j4 * 4;
-    L.offer(x.x, j + 0, valid, k, lane);
-    L.offer(x.y, j + 1, valid, k, lane);
-    L.offer(x.z, j + 2, valid, k, lane);
-    L.offer(x.w, j + 3, valid, k, lane);
+  // kU independent 16-byte loads per lane per batch, and the NEXT batch is already in flight while
+  // this one is examined (software pipelining); a whole batch is skipped with one vote when nothing
+  // in it can enter the current top-k
+  constexpr int kU = 4;
+  constexpr int kStride = kTopkWarps * 32 * kU;
+  const float4 kNegInf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  float4 x[kU], nx[kU];
+  int32_t base = warp * 32 * kU;
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const int32_t j4 = base + u * 32 + lane;
+    nx[u] = (base < n4 && j4 < n4) ? __ldg(row4 + j4) : kNegInf4;
+  }
+  for (; base < n4; base += kStride) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) x[u] = nx[u];
+    const int32_t nbase = base + kStride;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int32_t j4 = nbase + u * 32 + lane;
+      nx[u] = j4 < n4 ? __ldg(row4 + j4) : kNegInf4;
+    }
+    const float tv = __shfl_sync(0xffffffffu, L.v, k - 1);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) mx = fmaxf(mx, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+    if (!__any_sync(0xffffffffu, mx >= tv)) continue;  // >= : an equal value with a lower index still wins
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int32_t j4 = base + u * 32 + lane;
+      const bool valid = j4 < n4;
+      const int32_t j = j4 * 4;
+      const float um = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+      if (!__any_sync(0xffffffffu, valid && um >= tv)) continue;
+      L.offer(x[u].x, j + 0, valid, k, lane);
+      L.offer(x[u].y, j + 1, valid, k, lane);
+      L.offer(x[u].z, j + 2, valid, k, lane);
+      L.offer(x[u].w, j + 3, valid, k, lane);
+    }
   }
   for (int32_t base = n4 * 4 + warp * 32; base < n_g; base += kTopkWarps * 32) {
     const int32_t j = base + lane;

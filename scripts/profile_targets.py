@@ -1,0 +1,57 @@
+"""Launch every kernel of the path twice (warm-up + measured) at its BASELINE.json config size.
+Used under `ncu --set full -k regex:...`; prints nothing that should be read as a bench number."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from jegal_b200 import ops, synth
+
+dev = torch.device("cuda:0")
+which = set((sys.argv[1] if len(sys.argv) > 1 else "k0,k1,k2,k3,k4").split(","))
+reps = 2
+
+if which & {"k0", "k1", "k2"}:
+    Q, G, T, W = 1000, 65536, 64, 16
+    q, g, _ = synth.cfg5_gallery(Q, G, T, W, seed=1239, device=dev)
+    ql, gl = ops.Layout.from_lengths([T] * Q), ops.Layout.from_lengths([W] * G)
+    for _ in range(reps):
+        q16, _ = ops.prep(q, ql)
+        g16, _ = ops.prep(g, gl)  # K0 at 1.07 GB
+    if "k1" in which or "k2" in which:
+        for _ in range(reps):
+            s = ops.simpool_allpairs(q16, ql, g16, gl, "max_t_mean_w")  # K1 cfg5
+        for _ in range(reps):
+            ops.topk(s, 10)  # K2 1000 x 65536
+    del q, g, q16, g16
+if "k3" in which:
+    cs = synth.cfg3_spotting(20000, device=dev)
+    gl, cl = ops.Layout(cs.cu_t), ops.Layout(cs.cu_w)
+    g16, _ = ops.prep(cs.gest, gl)
+    c16, _ = ops.prep(cs.cont, cl)
+    wi = torch.from_numpy(cs.target_word).to(dev)
+    lo = torch.zeros(cs.n, dtype=torch.int32, device=dev)
+    hi = torch.full((cs.n,), 1000, dtype=torch.int32, device=dev)
+    for _ in range(reps):
+        ops.spot(g16, gl, c16, cl, wi, win_lo=lo, win_hi=hi)
+if "k4" in which:
+    ds = synth.cfg4_asd(10000, 4, device=dev)
+    cs = ds.clips
+    gl, cl = ops.Layout(cs.cu_t), ops.Layout(cs.cu_w)
+    g16, gs = ops.prep(cs.gest, gl, normalize=False, want_mean_scale=True, mean_eps=1e-8)
+    c16, cs_ = ops.prep(cs.cont, cl, normalize=False, want_mean_scale=True, mean_eps=1e-8)
+    pg, pc = torch.from_numpy(ds.pair_gest).to(dev), torch.from_numpy(ds.pair_cont).to(dev)
+    for _ in range(reps):
+        ops.simpool_pairs(g16, gl, c16, cl, pg, pc, "mean_mean", gscale=gs, cscale=cs_, group_size=4)
+if "k1cfg2" in which:
+    cs = synth.cfg2_retrieval(1000, device=dev)
+    gl, cl = ops.Layout(cs.cu_t), ops.Layout(cs.cu_w)
+    g16, _ = ops.prep(cs.gest, gl)
+    c16, _ = ops.prep(cs.cont, cl)
+    for mode in ("max_t_mean_w", "max_w_mean_t"):
+        for _ in range(reps):
+            ops.simpool_allpairs(g16, gl, c16, cl, mode)
+torch.cuda.synchronize()
+print("done")

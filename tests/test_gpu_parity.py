@@ -366,3 +366,20 @@ def test_cfg5_full_size_properties(dev):
         parts.append(ops.topk(ss, k, idx_offset=sh * per))
     mv, mi = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
     assert torch.equal(mi, i) and torch.equal(mv, v)
+
+
+# ----------------------------------------------------------------------------- host-streamed retrieval
+def test_streamed_retrieval_equals_resident(dev):
+    """Chunked H2D overlapped with compute + merge of per-chunk lists == one resident pass, bit for bit."""
+    from jegal_b200 import ops, streaming, synth
+    Q, G, T, W, k = 40, 5000, 64, 16, 10
+    q, g, gt = synth.cfg5_gallery(Q, G, T, W, seed=8)
+    ql = ops.Layout.from_lengths([T] * Q)
+    gal = streaming.StreamedGallery(g, np.full(G, W), chunk_clips=1024, device=dev)
+    v, i = streaming.retrieve_topk_streamed(q.pin_memory(), ql, gal, k=k)
+    gl = ops.Layout.from_lengths([W] * G)
+    q16, _ = ops.prep(q.to(dev), ql)
+    g16, _ = ops.prep(g.to(dev), gl)
+    rv, ri = ops.topk(ops.simpool_allpairs(q16, ql, g16, gl, "max_t_mean_w"), k)
+    assert torch.equal(i, ri) and torch.equal(v, rv)
+    assert np.array_equal(i[:, 0].cpu().numpy(), gt)
