@@ -9,8 +9,10 @@
 //   does "per frame over words" (softmax over words, evaluate_spotting.py:52-54;
 //   max over words) is register-local, and only per-frame scalars cross lanes.
 //
-//   warp 0  TMA producer: k-block ring (frames 32 rows per box so short clips do not
-//           drag 128 rows through L2; words 16 rows per box), runs ahead across items
+//   warp 0  TMA producer: frames 32 rows per box so short clips do not drag 128 rows through
+//           L2, words 16 rows per box.  Stages live in a byte ring and take exactly the
+//           bytes they load (a 69-frame x 8-word k-block is 14 KB, not a fixed 24 KB), so
+//           ~200 KB of payload — two to three clips — is in flight per SM, across items
 //   warp 1  tcgen05.mma issuer: M = 128, N = roundup16(W), 32 MMAs per row tile
 //   warp 2  TMEM allocator (4 accumulator buffers of 64 columns)
 //   warps 4-7 epilogue: tcgen05.ld -> softmax / pooling -> coalesced stores
@@ -26,11 +28,9 @@ using namespace ptx;
 namespace {
 
 constexpr int kGThreads = 256;
-constexpr int kGStages = 8;
+constexpr int kGStages = 32;                     // barrier slots; smem is a BYTE ring (see RingAlloc)
 constexpr int kNMax = 64;                        // words per clip on the N side
-constexpr uint32_t kGBytesG = 128 * 128;         // 128 frames x 64 elements x 2 B
-constexpr uint32_t kGBytesC = kNMax * 128;       // 64 words  x 64 elements x 2 B
-constexpr uint32_t kGStageBytes = kGBytesG + kGBytesC;
+constexpr uint32_t kGRingBytes = 216 * 1024;     // operand ring: a stage takes only the bytes it loads
 constexpr int kNumAcc = 4;
 constexpr uint32_t kGTmemCols = kNumAcc * kNMax;  // 256
 constexpr int kBoxG = 32, kBoxC = 16;
@@ -63,6 +63,13 @@ struct GroupedParams {
   float* scores;
 };
 
+// One tensor map per box height, so a stage is always exactly two TMA operations: frames in
+// boxes of 32/64/96/128 rows, words in boxes of 16/32/48/64 rows.
+struct alignas(64) GroupedMaps {
+  CUtensorMap g[4];
+  CUtensorMap c[4];
+};
+
 struct Item {
   int32_t g, c, g_row0, T, c_row0, W, n_rt, n16;
 };
@@ -80,18 +87,36 @@ __device__ __forceinline__ Item load_item(const GroupedParams& p, int32_t i) {
   return it;
 }
 
+// Deterministic byte-ring placement shared by the producer and the MMA issuer: both walk the same
+// item sequence, so both compute the same offsets.  A stage that would cross the end wraps to 0.
+struct RingAlloc {
+  uint32_t w = 0;
+  // returns the offset of a stage of `sz` bytes; `need` = bytes consumed including the wrap skip
+  __device__ __forceinline__ uint32_t place(uint32_t sz, uint32_t& need) {
+    uint32_t skip = 0;
+    // the MMA always reads 128 frame rows (16 KB) from the stage start, whatever was loaded:
+    // keep that window inside the ring (rows past the clip feed accumulator lanes nobody reads)
+    const uint32_t span = sz > 16384u ? sz : 16384u;
+    if (w + span > kGRingBytes) {
+      skip = kGRingBytes - w;
+      w = 0;
+    }
+    const uint32_t off = w;
+    w += sz;
+    need = skip + sz;
+    return off;
+  }
+};
+
 __device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int kEpi>
 __global__ void __launch_bounds__(kGThreads, 1)
-grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmC,
-               const GroupedParams p) {
+grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  const uint32_t bars = base + kGStages * kGStageBytes;
-  auto st_g = [&](int s) { return base + s * kGStageBytes; };
-  auto st_c = [&](int s) { return base + s * kGStageBytes + kGBytesG; };
+  const uint32_t bars = base + kGRingBytes;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (kGStages + s); };
   auto t_full = [&](int b) { return bars + 8u * (2 * kGStages + b); };
@@ -103,14 +128,12 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   constexpr int kScratchF = 4 * kNMax + 4;
   float* epi_f0 = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
   int32_t* epi_i0 = reinterpret_cast<int32_t*>(epi_f0 + 2 * kScratchF);
+  volatile uint32_t* need_smem = reinterpret_cast<volatile uint32_t*>(epi_i0 + 8);  // [kGStages], producer-private
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmG);
-    prefetch_tmap(&tmC);
-  }
+  if (warp == 0 && lane < 8) prefetch_tmap(lane < 4 ? &maps.g[lane] : &maps.c[lane - 4]);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kGStages; ++s) {
       mbar_init(full(s), 1);
@@ -131,57 +154,81 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   if (warp == 0) {
     if (elect_one()) {
       const uint64_t pol = policy_evict_first();  // every operand byte is used once
-      uint32_t s = 0, ph = 0;
+      // stage n uses barrier slot n % kGStages; `inflight` = ring bytes of stages not yet released.
+      // The bookkeeping of released bytes goes through a small smem array (need_smem).
+      uint32_t slot = 0, old_slot = 0, old_phase = 0, n_out = 0, inflight = 0;
+      RingAlloc ring;
       Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
       for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
         const Item it = nxt;
         // descriptor of the next item: its loads fly while this item's TMA is issued
         nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
+        const CUtensorMap* tmC = &maps.c[it.n16 - 1];
         for (int32_t rt = 0; rt < it.n_rt; ++rt) {
           const int32_t rows = min(128, it.T - rt * 128);
           const int32_t nb = (rows + kBoxG - 1) / kBoxG;
-          const uint32_t bytes = nb * (kBoxG * 128) + it.n16 * (kBoxC * 128);
+          const CUtensorMap* tmG = &maps.g[nb - 1];
+          const uint32_t bytes_g = nb * (kBoxG * 128);
+          const uint32_t bytes = bytes_g + it.n16 * (kBoxC * 128);
+          const int32_t g_row = it.g_row0 + rt * 128;
+#pragma unroll 1
           for (int kb = 0; kb < kNumKBlocks; ++kb) {
-            mbar_wait(empty(s), ph ^ 1u);
-            mbar_arrive_expect_tx(full(s), bytes);
-            for (int32_t b = 0; b < nb; ++b)
-              tma_load_2d(&tmG, full(s), st_g(s) + b * (kBoxG * 128), kb * kBlockK,
-                          it.g_row0 + rt * 128 + b * kBoxG, pol);
-            for (int32_t b = 0; b < it.n16; ++b)
-              tma_load_2d(&tmC, full(s), st_c(s) + b * (kBoxC * 128), kb * kBlockK, it.c_row0 + b * kBoxC, pol);
-            if (++s == kGStages) {
-              s = 0;
-              ph ^= 1u;
+            uint32_t need;
+            const uint32_t off = base + ring.place(bytes, need);
+            // free ring space / a barrier slot by retiring the oldest stages (the MMAs release in order)
+            while (inflight + need > kGRingBytes || n_out >= kGStages) {
+              mbar_wait(empty(old_slot), old_phase);
+              inflight -= need_smem[old_slot];
+              --n_out;
+              if (++old_slot == kGStages) {
+                old_slot = 0;
+                old_phase ^= 1u;
+              }
             }
+            need_smem[slot] = need;
+            inflight += need;
+            ++n_out;
+            const uint32_t fb = full(slot);
+            mbar_arrive_expect_tx(fb, bytes);
+            tma_load_2d(tmG, fb, off, kb * kBlockK, g_row, pol);
+            tma_load_2d(tmC, fb, off + bytes_g, kb * kBlockK, it.c_row0, pol);
+            if (++slot == kGStages) slot = 0;
           }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      uint32_t s = 0, ph = 0, tile = 0;
+      uint32_t slot = 0, phase = 0, tile = 0;
+      RingAlloc ring;
       Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
       for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
         const Item it = nxt;
         nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
         const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(it.n16 * 16) >> 3) << 17;
         for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
+          const int32_t rows = min(128, it.T - rt * 128);
+          const uint32_t bytes_g = ((rows + kBoxG - 1) / kBoxG) * (kBoxG * 128);
+          const uint32_t bytes = bytes_g + it.n16 * (kBoxC * 128);
           const uint32_t buf = tile % kNumAcc;
           mbar_wait(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kNMax;
+#pragma unroll 1
           for (int kb = 0; kb < kNumKBlocks; ++kb) {
-            mbar_wait(full(s), ph);
+            uint32_t need;
+            const uint32_t off = base + ring.place(bytes, need);
+            mbar_wait(full(slot), phase);
             tc_fence_after();
-            const uint64_t dG = make_smem_desc_sw128(st_g(s));
-            const uint64_t dC = make_smem_desc_sw128(st_c(s));
+            const uint64_t dG = make_smem_desc_sw128(off);
+            const uint64_t dC = make_smem_desc_sw128(off + bytes_g);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_f16<1>(d_tmem, dG + 2u * k, dC + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit<1>(empty(s));
-            if (++s == kGStages) {
-              s = 0;
-              ph ^= 1u;
+            umma_commit<1>(empty(slot));
+            if (++slot == kGStages) {
+              slot = 0;
+              phase ^= 1u;
             }
           }
           umma_commit<1>(t_full(buf));
@@ -245,19 +292,31 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
         const int32_t t = rt * 128 + et;
         const bool valid = t < it.T;
         if constexpr (kEpi == EPI_SPOT) {
-          // softmax over words of s / tau (evaluate_spotting.py:52-54), per frame
+          // softmax over words of s / tau (evaluate_spotting.py:52-54), per frame; only the
+          // 16-column groups that hold words are touched (W is uniform across the CTA)
           float m = -INFINITY;
 #pragma unroll
-          for (int w = 0; w < kNMax; ++w)
-            if (w < it.W) m = fmaxf(m, __uint_as_float(v[w]));
+          for (int g = 0; g < kNMax / 16; ++g) {
+            if (g < it.n16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (g * 16 + j < it.W) m = fmaxf(m, __uint_as_float(v[g * 16 + j]));
+            }
+          }
           float den = 0.f, pt = 0.f;
 #pragma unroll
-          for (int w = 0; w < kNMax; ++w) {
-            if (w < it.W) {
-              const float e = __expf((__uint_as_float(v[w]) - m) * p.inv_tau);
-              v[w] = __float_as_uint(e);
-              den += e;
-              if (w == target) pt = e;
+          for (int g = 0; g < kNMax / 16; ++g) {
+            if (g < it.n16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int w = g * 16 + j;
+                if (w < it.W) {
+                  const float e = __expf((__uint_as_float(v[w]) - m) * p.inv_tau);
+                  v[w] = __float_as_uint(e);
+                  den += e;
+                  if (w == target) pt = e;
+                }
+              }
             }
           }
           const float inv_den = 1.0f / den;
@@ -266,8 +325,15 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
             if (p.heat) p.heat[it.g_row0 + t] = pt;
             if (fh) {
 #pragma unroll
-              for (int w = 0; w < kNMax; ++w)
-                if (w < it.W) fh[static_cast<int64_t>(w) * it.T + t] = __uint_as_float(v[w]) * inv_den;
+              for (int g = 0; g < kNMax / 16; ++g) {
+                if (g < it.n16) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const int w = g * 16 + j;
+                    if (w < it.W) fh[static_cast<int64_t>(w) * it.T + t] = __uint_as_float(v[w]) * inv_den;
+                  }
+                }
+              }
             }
             if (pt > best_v) {  // frames arrive in increasing order: strict > keeps the first maximum
               best_v = pt;
@@ -278,23 +344,34 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
             // max over frames first: per word, reduce across the warp's valid lanes
 #pragma unroll
-            for (int w = 0; w < kNMax; ++w) {
-              if (w < it.W) {
-                float x = valid ? __uint_as_float(v[w]) : -INFINITY;
+            for (int g = 0; g < kNMax / 16; ++g) {
+              if (g < it.n16) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-                if (lane == (w & 31)) {
-                  if (w < 32) wmax0 = fmaxf(wmax0, x); else wmax1 = fmaxf(wmax1, x);
+                for (int j = 0; j < 16; ++j) {
+                  const int w = g * 16 + j;
+                  if (w < it.W) {
+                    float x = valid ? __uint_as_float(v[w]) : -INFINITY;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+                    if (lane == (w & 31)) {
+                      if (w < 32) wmax0 = fmaxf(wmax0, x); else wmax1 = fmaxf(wmax1, x);
+                    }
+                  }
                 }
               }
             }
           } else {
             float c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? 0.f : -INFINITY;
 #pragma unroll
-            for (int w = 0; w < kNMax; ++w) {
-              if (w < it.W) {
-                const float x = __uint_as_float(v[w]);
-                c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? c + x : fmaxf(c, x);
+            for (int g = 0; g < kNMax / 16; ++g) {
+              if (g < it.n16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (g * 16 + j < it.W) {
+                    const float x = __uint_as_float(v[g * 16 + j]);
+                    c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? c + x : fmaxf(c, x);
+                  }
+                }
               }
             }
             if (valid) racc = p.pool_mode == JEGAL_POOL_MAX_MAX ? fmaxf(racc, c) : racc + c;
@@ -384,8 +461,8 @@ grouped_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 }
 
 constexpr size_t grouped_smem_bytes() {
-  return 1024 + static_cast<size_t>(kGStages) * kGStageBytes + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
-         2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + 16;
+  return 1024 + static_cast<size_t>(kGRingBytes) + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
+         2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + sizeof(uint32_t) * kGStages + 16;
 }
 
 // one thread per group: softmax(scores / tau) within the group + first argmax
@@ -415,9 +492,19 @@ __global__ void group_softmax_kernel(const float* __restrict__ scores, int32_t n
   }
 }
 
+int make_grouped_maps(jegal_ctx* ctx, GroupedMaps* m, const void* gest_rows, int64_t gest_n, const void* cont_rows,
+                      int64_t cont_n, int op_dtype) {
+  for (int i = 0; i < 4; ++i) {
+    int rc = make_box_tmap_impl(ctx, &m->g[i], gest_rows, gest_n, op_dtype, kBoxG * (i + 1));
+    if (rc != JEGAL_OK) return rc;
+    rc = make_box_tmap_impl(ctx, &m->c[i], cont_rows, cont_n, op_dtype, kBoxC * (i + 1));
+    if (rc != JEGAL_OK) return rc;
+  }
+  return JEGAL_OK;
+}
+
 template <int kEpi>
-int launch_grouped(jegal_ctx* ctx, const CUtensorMap& tmG, const CUtensorMap& tmC, const GroupedParams& p,
-                   cudaStream_t stream) {
+int launch_grouped(jegal_ctx* ctx, const GroupedMaps& maps, const GroupedParams& p, cudaStream_t stream) {
   auto kern = grouped_kernel<kEpi>;
   constexpr size_t smem = grouped_smem_bytes();
   static bool configured = false;
@@ -427,7 +514,7 @@ int launch_grouped(jegal_ctx* ctx, const CUtensorMap& tmG, const CUtensorMap& tm
   }
   int grid = ctx->sm_count;
   if (p.n_items < grid) grid = p.n_items;
-  kern<<<grid, kGThreads, smem, stream>>>(tmG, tmC, p);
+  kern<<<grid, kGThreads, smem, stream>>>(maps, p);
   JEGAL_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;
   return JEGAL_OK;
@@ -486,12 +573,10 @@ int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest
   p.win_hi = win_hi_dev;
   p.thresh = thresh;
   p.correct = correct_dev;
-  CUtensorMap tmG, tmC;
-  rc = make_box_tmap_impl(ctx, &tmG, gest_rows_dev, gest_layout->rows, op_dtype, kBoxG);
+  GroupedMaps maps;
+  rc = make_grouped_maps(ctx, &maps, gest_rows_dev, gest_layout->rows, cont_rows_dev, cont_layout->rows, op_dtype);
   if (rc != JEGAL_OK) return rc;
-  rc = make_box_tmap_impl(ctx, &tmC, cont_rows_dev, cont_layout->rows, op_dtype, kBoxC);
-  if (rc != JEGAL_OK) return rc;
-  return launch_grouped<EPI_SPOT>(ctx, tmG, tmC, p, static_cast<cudaStream_t>(stream_));
+  return launch_grouped<EPI_SPOT>(ctx, maps, p, static_cast<cudaStream_t>(stream_));
 }
 
 int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
@@ -525,12 +610,10 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
   p.gscale = gscale_dev;
   p.cscale = cscale_dev;
   p.scores = scores_dev;
-  CUtensorMap tmG, tmC;
-  rc = make_box_tmap_impl(ctx, &tmG, gest_rows_dev, gest_layout->rows, op_dtype, kBoxG);
+  GroupedMaps maps;
+  rc = make_grouped_maps(ctx, &maps, gest_rows_dev, gest_layout->rows, cont_rows_dev, cont_layout->rows, op_dtype);
   if (rc != JEGAL_OK) return rc;
-  rc = make_box_tmap_impl(ctx, &tmC, cont_rows_dev, cont_layout->rows, op_dtype, kBoxC);
-  if (rc != JEGAL_OK) return rc;
-  rc = launch_grouped<EPI_POOL>(ctx, tmG, tmC, p, stream);
+  rc = launch_grouped<EPI_POOL>(ctx, maps, p, stream);
   if (rc != JEGAL_OK) return rc;
   if (want_groups) {
     const int32_t n_groups = n_pairs / group_size;
