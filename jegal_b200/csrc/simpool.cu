@@ -131,11 +131,14 @@ __device__ __forceinline__ void emit(float acc, int32_t cclip, bool col_partial,
 }
 
 // Pool one 32-column chunk of this thread's row: `em` marks the columns that end a segment.
+// Works in 8-column sub-blocks: a sub-block whose only possible segment end is its last column is
+// a 4-instruction tree reduction; one with an interior end is split into runs with 8-wide masks.
+// All branches are warp-uniform (every row of the tile sees the same column segmentation).
 template <int kColOp, int kRowOp>
 __device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em, float& acc, int32_t& cclip,
                                            bool col_partial, const RowCtx& rc, const SimpoolParams& p) {
   if ((em & 0x7f7f7f7fu) == 0u) {
-    // fast path: segment ends (if any) only at columns 7/15/23/31 of the chunk
+    // whole chunk on the fast path (config 5: every chunk): no per-sub-block tests
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
@@ -145,27 +148,39 @@ __device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em,
         acc = op_ident<kColOp>();
       }
     }
-  } else {
-    // general path: one masked reduction per run of columns between segment ends
-    uint32_t rem = em;
-    uint32_t start = 0;
-    while (true) {
-      const uint32_t e = rem ? static_cast<uint32_t>(__ffs(rem) - 1) : 31u;
-      const uint32_t m = (e == 31u ? 0xffffffffu : ((1u << (e + 1)) - 1u)) & ~((1u << start) - 1u);
-      float r = op_ident<kColOp>();
+    return;
+  }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = ((m >> j) & 1u) ? __uint_as_float(v[j]) : op_ident<kColOp>();
-        r = op_apply<kColOp>(r, x);
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t em8 = (em >> (8 * j)) & 0xffu;
+    if ((em8 & 0x7fu) == 0u) {
+      acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
+      if (em8 & 0x80u) {
+        emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+        ++cclip;
+        acc = op_ident<kColOp>();
       }
-      acc = op_apply<kColOp>(acc, r);
-      if (!rem) break;
-      emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
-      ++cclip;
-      acc = op_ident<kColOp>();
-      rem &= rem - 1u;
-      start = e + 1u;
-      if (start >= 32u) break;
+    } else {
+      uint32_t rem = em8;
+      uint32_t start = 0;
+      while (true) {
+        const uint32_t e = rem ? static_cast<uint32_t>(__ffs(rem) - 1) : 7u;
+        const uint32_t m = ((2u << e) - 1u) & ~((1u << start) - 1u);  // columns start..e of the sub-block
+        float r = op_ident<kColOp>();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = ((m >> i) & 1u) ? __uint_as_float(v[8 * j + i]) : op_ident<kColOp>();
+          r = op_apply<kColOp>(r, x);
+        }
+        acc = op_apply<kColOp>(acc, r);
+        if (!rem) break;
+        emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+        ++cclip;
+        acc = op_ident<kColOp>();
+        rem &= rem - 1u;
+        start = e + 1u;
+        if (start >= 8u) break;
+      }
     }
   }
 }
