@@ -198,6 +198,8 @@ def main_ours(args, wl, rank, local_rank, world):
     ev_k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
              for _ in range(args.steps)]
 
+    ex = ops.TopkExchange(Q, k) if (world > 1 and args.exchange == "p2p") else None
+
     def step(i_timed=None):
         qr = sharded.broadcast_queries(q_raw, Q * T, torch.float16, dev) if world > 1 else q_raw
         ops.prep(qr, q_layout, out=q16)
@@ -207,6 +209,8 @@ def main_ours(args, wl, rank, local_rank, world):
         ops.simpool_allpairs(q16, q_layout, g16, s_layout, mode, out=scores)
         if i_timed is not None:
             ev_k1[i_timed][1].record()
+        if ex is not None:
+            return ex.topk(scores, idx_offset=lo)  # K2 + NVLink exchange + merge, two kernels
         v, i = ops.topk(scores, k, idx_offset=lo)
         if world > 1:
             vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
@@ -308,7 +312,9 @@ def main_ours(args, wl, rank, local_rank, world):
         "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": wl["desc"] + (f"; gallery x{world} (weak)" if weak else "; gallery sharded by clip over the GPUs"),
-            "step": "K0 prep(queries)+K0 prep(gallery shard)+K1 fused sim-pool+K2 top-k" + ("+all-gather+merge" if world > 1 else ""),
+            "step": "K0 prep(queries)+K0 prep(gallery shard)+K1 fused sim-pool+K2 top-k" + (
+                "" if world == 1 else "+NVLink peer-memory exchange+merge (fused, csrc/exchange.cu)" if ex is not None
+                else "+NCCL all-gather+merge"),
             "inputs": "raw fp16 unit-norm embeddings resident in HBM; bf16 operands, fp32 accumulate in TMEM",
             "l2": "no flush needed: the 1.07 GB gallery (>= 134 MB per shard) exceeds the 126 MB L2 every step",
             "parallelism": f"gallery-sharded x{world}", "recall_at_1_planted": recall1,
@@ -343,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU top-k exchange: fused NVLink peer-memory kernels (p2p) or NCCL all-gather + merge")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

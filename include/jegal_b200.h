@@ -162,6 +162,24 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
                         int32_t group_size, float tau, float* scores_dev, float* probs_dev,
                         int32_t* argmax_dev, void* stream);
 
+/* C1 — top-k exchange between the GPUs of one box over NVLink peer memory, fused into K2
+ * (no reference counterpart: the reference has no multi-GPU code).
+ * Every rank creates an exchange block, publishes its 64-byte CUDA IPC handle, receives the handles
+ * of all ranks (rank-major, world * 64 bytes; any transport — torch.distributed in jegal_b200/ops.py)
+ * and connects.  jegal_topk_exchange then runs per-query top-k on this rank's score shard
+ * [n_q, n_g], stores the k (value, global index) pairs into every peer's block with plain global
+ * stores on the IPC-mapped pointers, publishes a sequence flag (system-scope release), waits for the
+ * flags of all ranks and merges the world lists locally: out = the global top-k, identical on
+ * every rank and identical to a single-GPU jegal_topk over the concatenated shards. */
+typedef struct jegal_exchange jegal_exchange;
+int jegal_exchange_create(jegal_ctx* ctx, int32_t rank, int32_t world, int32_t n_q, int32_t k,
+                          jegal_exchange** out);
+int jegal_exchange_ipc_handle(const jegal_exchange* ex, void* handle_out_64B);
+int jegal_exchange_connect(jegal_exchange* ex, const void* all_handles);
+void jegal_exchange_destroy(jegal_exchange* ex);
+int jegal_topk_exchange(jegal_ctx* ctx, jegal_exchange* ex, const float* scores_dev, int32_t n_g, int64_t ld,
+                        int32_t idx_offset, float* out_val_dev, int32_t* out_idx_dev, void* stream);
+
 /* softmax(scores / tau) and first argmax inside groups: group g covers
  * scores[g * stride .. g * stride + group_size).  stride >= group_size lets a caller score
  * prefixes of a wider candidate list (evaluate_asd.py:94-100 scores the first 2, 4, 6).

@@ -33,6 +33,11 @@ SYMBOLS = [
     "jegal_spot",
     "jegal_simpool_pairs",
     "jegal_group_softmax",
+    "jegal_exchange_create",
+    "jegal_exchange_ipc_handle",
+    "jegal_exchange_connect",
+    "jegal_exchange_destroy",
+    "jegal_topk_exchange",
 ]
 
 F32, F16, BF16 = 0, 1, 2
@@ -101,6 +106,13 @@ def load() -> C.CDLL:
         lib.jegal_simpool_pairs.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]
     if hasattr(lib, "jegal_group_softmax"):
         lib.jegal_group_softmax.argtypes = [vp, vp, i32, i32, i64, f32, vp, vp, vp]
+    if hasattr(lib, "jegal_topk_exchange"):
+        lib.jegal_exchange_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
+        lib.jegal_exchange_ipc_handle.argtypes = [vp, vp]
+        lib.jegal_exchange_connect.argtypes = [vp, vp]
+        lib.jegal_exchange_destroy.argtypes = [vp]
+        lib.jegal_exchange_destroy.restype = None
+        lib.jegal_topk_exchange.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("jegal_layout_clips",):

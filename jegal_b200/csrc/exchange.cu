@@ -1,0 +1,305 @@
+// C1 — top-k exchange between the GPUs of one box over NVLink peer memory, fused into K2.
+//
+// The gallery is sharded by clip; after K1 every rank holds scores [Q, G_local].  Instead of
+// "K2, then an NCCL all-gather, then a merge", ONE pair of kernels does the exchange itself:
+//
+//   topk_exchange_kernel   per-query top-k of the local shard (same code path as K2); the final
+//                          k (value, global index) pairs are stored straight into EVERY peer's
+//                          exchange block (slot = this rank) with ordinary st.global on
+//                          IPC-mapped peer pointers — the stores travel over NVLink/NVSwitch;
+//                          the last block to finish publishes a per-rank sequence flag to every
+//                          peer (system-scope release);
+//   topk_merge_wait_kernel waits (system-scope acquire) until every rank's flag carries this
+//                          step's sequence number, then merges the world lists that sit in LOCAL
+//                          memory with K2's ordering rule (score desc, ties to lower global index).
+//
+// Two block parities alternate, which makes the protocol self-synchronising: a rank can only
+// finish step s+1 after every peer published s+1, i.e. after every peer finished reading step s.
+// The payload is tiny (Q*k*8 B per rank: 80 KB for config 5) — this path is latency-, not
+// bandwidth-bound, and saves two host-launched collectives per step.
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+struct jegal_exchange {
+  jegal_ctx* ctx = nullptr;
+  int32_t rank = 0, world = 1, n_q = 0, k = 0;
+  uint8_t* local = nullptr;  // cudaMalloc'ed exchange block of this rank
+  size_t bytes = 0;
+  uint8_t* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool opened[8] = {false, false, false, false, false, false, false, false};
+  uint32_t seq = 0;
+};
+
+namespace jegal {
+namespace {
+
+constexpr int kMaxWorld = 8;
+constexpr size_t kHdrBytes = 256;  // [0,64): flags[parity][world] u32   [128]: block counter
+
+struct ExView {
+  uint8_t* base[kMaxWorld];
+};
+
+__host__ __device__ inline size_t ex_list_elems(int world, int n_q, int k) {
+  return static_cast<size_t>(world) * n_q * k;
+}
+// block layout: header | vals[2][world][n_q][k] f32 | idxs[2][world][n_q][k] i32
+__host__ __device__ inline size_t ex_vals_off(int parity, int world, int n_q, int k) {
+  return kHdrBytes + parity * ex_list_elems(world, n_q, k) * 4;
+}
+__host__ __device__ inline size_t ex_idxs_off(int parity, int world, int n_q, int k) {
+  return kHdrBytes + 2 * ex_list_elems(world, n_q, k) * 4 + parity * ex_list_elems(world, n_q, k) * 4;
+}
+
+__device__ __forceinline__ bool better(float av, int32_t ai, float bv, int32_t bi) {
+  return av > bv || (av == bv && ai < bi);
+}
+
+struct WarpList {  // same structure as in topk.cu: a descending 32-entry list across the lanes of a warp
+  float v;
+  int32_t i;
+  __device__ __forceinline__ void init() {
+    v = -INFINITY;
+    i = 0x7fffffff;
+  }
+  __device__ __forceinline__ void insert(float cv, int32_t ci, int lane) {
+    const bool worse = better(cv, ci, v, i);
+    const uint32_t wm = __ballot_sync(0xffffffffu, worse);
+    const int pos = __ffs(wm) - 1;
+    const float upv = __shfl_up_sync(0xffffffffu, v, 1);
+    const int32_t upi = __shfl_up_sync(0xffffffffu, i, 1);
+    if (pos >= 0) {
+      if (lane > pos) {
+        v = upv;
+        i = upi;
+      } else if (lane == pos) {
+        v = cv;
+        i = ci;
+      }
+    }
+  }
+  __device__ __forceinline__ void offer(float cv, int32_t ci, bool valid, int k, int lane) {
+    float tv = __shfl_sync(0xffffffffu, v, k - 1);
+    int32_t ti = __shfl_sync(0xffffffffu, i, k - 1);
+    uint32_t m = __ballot_sync(0xffffffffu, valid && better(cv, ci, tv, ti));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float bv = __shfl_sync(0xffffffffu, cv, src);
+      const int32_t bi = __shfl_sync(0xffffffffu, ci, src);
+      if (better(bv, bi, tv, ti)) {
+        insert(bv, bi, lane);
+        tv = __shfl_sync(0xffffffffu, v, k - 1);
+        ti = __shfl_sync(0xffffffffu, i, k - 1);
+      }
+    }
+  }
+};
+
+constexpr int kXWarps = 4;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// one block per query row; the result goes to every peer's block (slot = rank)
+__global__ void __launch_bounds__(kXWarps * 32)
+topk_exchange_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k, int32_t idx_offset,
+                     ExView peers, int32_t rank, int32_t world, int32_t n_q, uint32_t seq) {
+  __shared__ float sv[kXWarps][32];
+  __shared__ int32_t si[kXWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = blockIdx.x;
+  const float* row = scores + q * ld;
+  WarpList L;
+  L.init();
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+  const int32_t n4 = vec_ok ? (n_g >> 2) : 0;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  for (int32_t base = warp * 32; base < n4; base += kXWarps * 32) {
+    const int32_t j4 = base + lane;
+    const bool valid = j4 < n4;
+    const float4 x = valid ? __ldg(row4 + j4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const float tv = __shfl_sync(0xffffffffu, L.v, k - 1);
+    const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    if (!__any_sync(0xffffffffu, valid && mx >= tv)) continue;
+    const int32_t j = j4 * 4;
+    L.offer(x.x, j + 0, valid, k, lane);
+    L.offer(x.y, j + 1, valid, k, lane);
+    L.offer(x.z, j + 2, valid, k, lane);
+    L.offer(x.w, j + 3, valid, k, lane);
+  }
+  for (int32_t base = n4 * 4 + warp * 32; base < n_g; base += kXWarps * 32) {
+    const int32_t j = base + lane;
+    const bool valid = j < n_g;
+    L.offer(valid ? __ldg(row + j) : 0.f, j, valid, k, lane);
+  }
+  sv[warp][lane] = L.v;
+  si[warp][lane] = L.i;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kXWarps; ++w) L.offer(sv[w][lane], si[w][lane], lane < k, k, lane);
+    const int parity = seq & 1u;
+    if (lane < k) {
+      const bool real = L.i != 0x7fffffff;
+      const int32_t gi = real ? L.i + idx_offset : -1;
+      const size_t slot = (static_cast<size_t>(rank) * n_q + q) * k + lane;
+      for (int p = 0; p < world; ++p) {  // NVLink stores into every peer's exchange block
+        float* pv = reinterpret_cast<float*>(peers.base[p] + ex_vals_off(parity, world, n_q, k));
+        int32_t* pi = reinterpret_cast<int32_t*>(peers.base[p] + ex_idxs_off(parity, world, n_q, k));
+        pv[slot] = L.v;
+        pi[slot] = gi;
+      }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t* counter = reinterpret_cast<uint32_t*>(peers.base[rank] + 128);
+      const uint32_t done = atomicAdd(counter, 1u);
+      if (done == gridDim.x - 1) {  // every block's lists are out: publish this rank's flag everywhere
+        *counter = 0;
+        __threadfence_system();
+        for (int p = 0; p < world; ++p)
+          st_release_sys(reinterpret_cast<uint32_t*>(peers.base[p]) + parity * kMaxWorld + rank, seq);
+      }
+    }
+  }
+}
+
+// one warp per query: wait for all ranks' flags, then merge the lists in local memory
+__global__ void __launch_bounds__(128)
+topk_merge_wait_kernel(const uint8_t* __restrict__ local, int32_t world, int32_t n_q, int32_t k, uint32_t seq,
+                       float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  const int parity = seq & 1u;
+  if (threadIdx.x < world) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(local) + parity * kMaxWorld + threadIdx.x;
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - seq) < 0) {
+      if (++spins > (1u << 26)) {
+        printf("jegal: exchange watchdog: rank flag %d never reached seq %u\n", (int)threadIdx.x, seq);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_q) return;
+  const float* vals = reinterpret_cast<const float*>(local + ex_vals_off(parity, world, n_q, k));
+  const int32_t* idxs = reinterpret_cast<const int32_t*>(local + ex_idxs_off(parity, world, n_q, k));
+  WarpList L;
+  L.init();
+  for (int32_t l = 0; l < world; ++l) {
+    const size_t off = (static_cast<size_t>(l) * n_q + q) * k;
+    const bool valid = lane < k;
+    const float cv = valid ? __ldcg(vals + off + lane) : 0.f;  // written by peers: bypass L1
+    const int32_t ci = valid ? __ldcg(idxs + off + lane) : 0;
+    L.offer(cv, ci, valid && ci >= 0, k, lane);
+  }
+  if (lane < k) {
+    const bool real = L.i != 0x7fffffff;
+    out_val[static_cast<int64_t>(q) * k + lane] = L.v;
+    out_idx[static_cast<int64_t>(q) * k + lane] = real ? L.i : -1;
+  }
+}
+
+}  // namespace
+}  // namespace jegal
+
+using namespace jegal;
+
+extern "C" {
+
+int jegal_exchange_create(jegal_ctx* ctx, int32_t rank, int32_t world, int32_t n_q, int32_t k,
+                          jegal_exchange** out) {
+  if (!ctx || !out) return set_err(ctx, JEGAL_ERR_ARG, "exchange_create: null argument");
+  *out = nullptr;
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_q < 1 || k < 1 || k > 32)
+    return set_err(ctx, JEGAL_ERR_ARG, "exchange_create: need 1 <= world <= 8, 0 <= rank < world, n_q >= 1, 1 <= k <= 32");
+  auto* ex = new (std::nothrow) jegal_exchange();
+  if (!ex) return set_err(ctx, JEGAL_ERR_NOMEM, "out of host memory");
+  ex->ctx = ctx;
+  ex->rank = rank;
+  ex->world = world;
+  ex->n_q = n_q;
+  ex->k = k;
+  ex->bytes = kHdrBytes + 4 * ex_list_elems(world, n_q, k) * 4;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->local, ex->bytes);
+  if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->bytes);
+  if (e != cudaSuccess) {
+    if (ex->local) cudaFree(ex->local);
+    delete ex;
+    return set_err(ctx, JEGAL_ERR_CUDA, std::string("exchange_create: ") + cudaGetErrorString(e));
+  }
+  ex->peer[rank] = ex->local;
+  *out = ex;
+  return JEGAL_OK;
+}
+
+int jegal_exchange_ipc_handle(const jegal_exchange* ex, void* handle_out_64B) {
+  if (!ex || !handle_out_64B) return JEGAL_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, ex->local);
+  if (e != cudaSuccess) return set_err(ex->ctx, JEGAL_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  std::memcpy(handle_out_64B, &h, 64);
+  return JEGAL_OK;
+}
+
+int jegal_exchange_connect(jegal_exchange* ex, const void* all_handles) {
+  if (!ex || !all_handles) return JEGAL_ERR_ARG;
+  cudaSetDevice(ex->ctx->device);
+  for (int p = 0; p < ex->world; ++p) {
+    if (p == ex->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const uint8_t*>(all_handles) + 64 * p, 64);
+    void* ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return set_err(ex->ctx, JEGAL_ERR_CUDA, "cudaIpcOpenMemHandle(rank " + std::to_string(p) + "): " + cudaGetErrorString(e));
+    ex->peer[p] = static_cast<uint8_t*>(ptr);
+    ex->opened[p] = true;
+  }
+  return JEGAL_OK;
+}
+
+void jegal_exchange_destroy(jegal_exchange* ex) {
+  if (!ex) return;
+  for (int p = 0; p < kMaxWorld; ++p)
+    if (ex->opened[p]) cudaIpcCloseMemHandle(ex->peer[p]);
+  if (ex->local) cudaFree(ex->local);
+  delete ex;
+}
+
+int jegal_topk_exchange(jegal_ctx* ctx, jegal_exchange* ex, const float* scores_dev, int32_t n_g, int64_t ld,
+                        int32_t idx_offset, float* out_val_dev, int32_t* out_idx_dev, void* stream_) {
+  if (!ctx || !ex || !out_val_dev || !out_idx_dev || (!scores_dev && n_g > 0))
+    return set_err(ctx, JEGAL_ERR_ARG, "topk_exchange: null argument");
+  if (n_g < 0 || ld < n_g) return set_err(ctx, JEGAL_ERR_ARG, "topk_exchange: bad shape");
+  for (int p = 0; p < ex->world; ++p)
+    if (!ex->peer[p]) return set_err(ctx, JEGAL_ERR_ARG, "topk_exchange: exchange not connected (jegal_exchange_connect)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ex->seq += 1;
+  ExView view;
+  for (int p = 0; p < kMaxWorld; ++p) view.base[p] = ex->peer[p];
+  topk_exchange_kernel<<<static_cast<unsigned>(ex->n_q), kXWarps * 32, 0, stream>>>(
+      scores_dev, n_g, ld, ex->k, idx_offset, view, ex->rank, ex->world, ex->n_q, ex->seq);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  const int warps = 4;
+  topk_merge_wait_kernel<<<static_cast<unsigned>((ex->n_q + warps - 1) / warps), warps * 32, 0, stream>>>(
+      ex->local, ex->world, ex->n_q, ex->k, ex->seq, out_val_dev, out_idx_dev);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
+
+}  // extern "C"

@@ -329,3 +329,56 @@ def group_softmax(scores: torch.Tensor, n_groups: int, group_size: int, stride: 
                                      _ptr(argmax), _stream())
     ctx.check(rc, "jegal_group_softmax")
     return probs, argmax
+
+
+class TopkExchange:
+    """C1: K2 + NVLink peer-memory exchange + merge for a gallery sharded over the ranks of one box.
+
+    Construction is collective (every rank of ``group`` must call it): the CUDA IPC handles of the
+    per-rank exchange blocks are all-gathered through torch.distributed and opened.
+    """
+
+    def __init__(self, n_q: int, k: int, group=None, device: Optional[int] = None):
+        import torch.distributed as dist
+
+        self.ctx = Context.get(device)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_q, self.k = int(n_q), int(k)
+        h = C.c_void_p()
+        rc = self.ctx.lib.jegal_exchange_create(self.ctx.h, self.rank, self.world, self.n_q, self.k, C.byref(h))
+        self.ctx.check(rc, "jegal_exchange_create")
+        self.h = h
+        mine = (C.c_uint8 * 64)()
+        self.ctx.check(self.ctx.lib.jegal_exchange_ipc_handle(self.h, mine), "jegal_exchange_ipc_handle")
+        handles = [bytes(mine)]
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine), group=group)
+            handles = gathered
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.ctx.check(self.ctx.lib.jegal_exchange_connect(self.h, buf), "jegal_exchange_connect")
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def topk(self, scores: torch.Tensor, idx_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """scores: this rank's [n_q, n_local] fp32 shard.  Returns the GLOBAL top-k on every rank."""
+        if not scores.is_cuda or scores.dtype != torch.float32 or scores.dim() != 2 or scores.shape[0] != self.n_q:
+            raise JegalError("TopkExchange.topk: expected CUDA fp32 [n_q, n_local]")
+        if scores.shape[1] > 0 and scores.stride(1) != 1:
+            raise JegalError("TopkExchange.topk: unit column stride required")
+        val = torch.empty((self.n_q, self.k), dtype=torch.float32, device=scores.device)
+        idx = torch.empty((self.n_q, self.k), dtype=torch.int32, device=scores.device)
+        rc = self.ctx.lib.jegal_topk_exchange(self.ctx.h, self.h, _ptr(scores), scores.shape[1],
+                                              max(scores.stride(0), scores.shape[1]), idx_offset, _ptr(val), _ptr(idx), _stream())
+        self.ctx.check(rc, "jegal_topk_exchange")
+        return val, idx
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.ctx.lib.jegal_exchange_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

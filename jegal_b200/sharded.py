@@ -10,10 +10,14 @@ N-GPU result equals the 1-GPU result bit for bit on the indices.
 The reference has no counterpart (no torch.distributed anywhere in it).
 
 Two exchange paths:
-  * ``exchange="nccl"``   one all-gather of [Q, k] values + one of indices, then K2-merge;
-  * ``exchange="p2p"``    K2 writes each rank's list straight into every peer's symmetric
-                          buffer over NVLink (no host-launched collective on the data path),
-                          followed by a symmetric-memory barrier and the local K2-merge.
+  * ``retrieve_topk_sharded(..)``                 K2, one all-gather of [Q, k] values + one of
+                                                  indices (NCCL), then the K2 merge kernel;
+  * ``retrieve_topk_sharded(.., exchange=ex)``    with ``ex = ops.TopkExchange(Q, k)``: K2 stores each
+                                                  rank's list straight into every peer's exchange block
+                                                  over NVLink (IPC-mapped pointers), publishes a flag,
+                                                  and the merge kernel waits on the flags — no
+                                                  host-launched collective on the data path
+                                                  (csrc/exchange.cu).
 
 The local scoring / merge functions are injectable so the host logic (sharding,
 offsets, collectives) is covered on CPU with the gloo backend in tests/.
@@ -72,12 +76,23 @@ def retrieve_topk_sharded(
     group: Optional[dist.ProcessGroup] = None,
     local_topk_fn: Callable = _cuda_local_topk,
     merge_fn: Callable = _cuda_merge,
+    exchange=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Every rank returns the same merged (values [Q, k], global indices [Q, k]).
 
     ``q16`` are the replicated, prepped query rows; ``shard16`` / ``shard_layout`` this rank's
     gallery clips, whose first clip has global index ``shard_lo``.
     """
+    if exchange is not None:  # fused K2 + NVLink exchange + merge
+        from . import ops
+
+        if shard_layout.n_clips == 0:
+            s = torch.empty((q_layout.n_clips, 0), dtype=torch.float32, device=q16.device)
+        elif queries_are == "gesture":
+            s = ops.simpool_allpairs(q16, q_layout, shard16, shard_layout, mode)
+        else:
+            s = ops.simpool_allpairs(shard16, shard_layout, q16, q_layout, mode, content_major=True)
+        return exchange.topk(s, idx_offset=shard_lo)
     v, i = local_topk_fn(q16, q_layout, shard16, shard_layout, k, mode, shard_lo, queries_are)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:

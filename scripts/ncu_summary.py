@@ -9,6 +9,7 @@ KEYS = [
     ("gpu__time_duration.sum", "duration"),
     ("sm__cycles_elapsed.avg.per_second", "SM clock"),
     ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (elapsed)"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor memory (TMEM) active % (elapsed)"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
     ("dram__bytes_read.sum", "dram bytes read"),
@@ -34,6 +35,8 @@ def main(path):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
+    for h, i in list(col.items()):  # some metrics carry a "TPC.TriageCompute." style prefix
+        col.setdefault(h.split(".", 2)[-1] if h.startswith(("TPC.", "SM_", "LTS.")) else h, i)
     print(f"# ncu summary of `{path}`\n")
     print("Per profiled launch (`ncu --set full --clock-control none`, cold caches, serialised replays —")
     print("compare shares and ratios, not absolute times, with the CUDA-event numbers in bench.py).\n")

@@ -11,7 +11,7 @@ from jegal_b200 import ops, synth
 
 dev = torch.device("cuda:0")
 which = set((sys.argv[1] if len(sys.argv) > 1 else "k0,k1,k2,k3,k4").split(","))
-reps = 2
+reps = int(os.environ.get("PROFILE_REPS", 2))
 
 if which & {"k0", "k1", "k2"}:
     Q, G, T, W = 1000, 65536, 64, 16

@@ -383,3 +383,14 @@ def test_streamed_retrieval_equals_resident(dev):
     rv, ri = ops.topk(ops.simpool_allpairs(q16, ql, g16, gl, "max_t_mean_w"), k)
     assert torch.equal(i, ri) and torch.equal(v, rv)
     assert np.array_equal(i[:, 0].cpu().numpy(), gt)
+
+
+def test_topk_exchange_single_rank(dev):
+    """World-size-1 exchange (self slot only) == plain K2: covers the fused kernels and the flag protocol."""
+    from jegal_b200 import ops
+    x = torch.randint(0, 30, (50, 3000), device=dev).float()
+    ex = ops.TopkExchange(50, 10)
+    for _ in range(3):
+        v, i = ex.topk(x, idx_offset=5)
+        rv, ri = ops.topk(x, 10, idx_offset=5)
+        assert torch.equal(i, ri) and torch.equal(v, rv)

@@ -35,6 +35,11 @@ def _worker(rank, world, port, ret):
         rv, ri = ops.topk(ops.simpool_allpairs(q16, ql, g16, gl, "max_t_mean_w"), k)
         assert torch.equal(i, ri) and torch.equal(v, rv)
         assert np.array_equal(i[:, 0].cpu().numpy(), gt)
+        # fused K2 + NVLink peer-memory exchange + merge (no NCCL on the data path), several steps in a row
+        ex = ops.TopkExchange(Q, k)
+        for step in range(5):
+            pv, pi = sharded.retrieve_topk_sharded(q16, ql, s16, sl, lo, k=k, exchange=ex)
+            assert torch.equal(pi, ri) and torch.equal(pv, rv), f"p2p exchange differs at step {step}"
         ret[rank] = True
     finally:
         dist.destroy_process_group()
