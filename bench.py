@@ -304,6 +304,11 @@ def main_ours(args, wl, rank, local_rank, world):
         if not args.no_e2e:  # the streamed host path must return the very same lists
             assert np.array_equal(hi_.numpy(), i.cpu().numpy()), "e2e top-k differs from the resident path"
     peaks = load_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic_r01.json")
+    if world == 1 and os.path.exists(tpath):  # from the committed ncu --set full capture of this very launch shape
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
     flops = 2.0 * 512 * (Q * T) * (n_shard * W)  # algorithmic flops of ONE K1 launch on this rank's shard
     achieved = flops / (k1_ms * 1e-3) / 1e12
     line = {
@@ -328,7 +333,8 @@ def main_ours(args, wl, rank, local_rank, world):
                      "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                      "frac_of_sustained": achieved / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None,
                      "peak_source": peaks["source"] + ", burst bf16 figure", "k1_ms": k1_ms,
-                     "algorithmic_flops_per_launch": flops, "traffic": None},
+                     "algorithmic_flops_per_launch": flops, "traffic": traffic,
+                     "traffic_unit": "bytes (dram read+write per launch, ncu; profiles/k1_traffic_r01.json)"},
     }
     if world == 1 and not args.no_cpu:
         g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 1024))
