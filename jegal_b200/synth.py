@@ -129,20 +129,20 @@ def cfg1_samples(seed: int = 1235, device="cpu") -> ClipSet:
     return make_clipset(lt, lw, seed, device, boundaries=[c[1] for c in SAMPLE_CLIPS], with_targets=True)
 
 
-def cfg2_retrieval(n: int = 1000, seed: int = 1236, device="cpu") -> ClipSet:
+def cfg2_retrieval(n: int = 1000, seed: int = 1236, device="cpu", **kw) -> ClipSet:
     """AVS-Ret-shaped: T ~ U{25..200}, W ~ U{4..40}."""
     rng = np.random.default_rng(seed)
     lt = rng.integers(25, 201, size=n)
     lw = np.minimum(rng.integers(4, 41, size=n), lt)
-    return make_clipset(lt, lw, seed, device)
+    return make_clipset(lt, lw, seed, device, **kw)
 
 
-def cfg3_spotting(n: int = 20000, seed: int = 1237, device="cpu") -> ClipSet:
+def cfg3_spotting(n: int = 20000, seed: int = 1237, device="cpu", **kw) -> ClipSet:
     """AVS-Spot-shaped: T in 25..220 (mean ~69), W in 4..12, one target word per clip."""
     rng = np.random.default_rng(seed)
     lt = np.clip(25 + rng.gamma(shape=2.2, scale=20.0, size=n), 25, 220).astype(np.int64)
     lw = rng.integers(4, 13, size=n)
-    return make_clipset(lt, lw, seed, device, with_targets=True)
+    return make_clipset(lt, lw, seed, device, with_targets=True, **kw)
 
 
 @dataclass

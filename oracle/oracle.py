@@ -106,7 +106,7 @@ def get_attn_matrix(gesture, content, temp: float = TEMP, normalize: bool = True
         c = F.normalize(c, p=2, dim=-1)
     a = torch.mm(g, c.t()) / temp
     a = F.softmax(a, dim=1)
-    return np.array(a).T
+    return a.numpy().T  # == np.array(attn_mat).T of the reference (a transposed view)
 
 
 def spot_decision(attn: np.ndarray, word_idx: int, start: int, end: int, thresh: float = 0.5,
