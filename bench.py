@@ -257,7 +257,7 @@ def main_ours(args, wl, rank, local_rank, world):
     from jegal_b200 import streaming
 
     q_host = q_raw.cpu().pin_memory() if rank == 0 or world == 1 else None
-    gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), chunk_clips=max(1024, n_shard // 8),
+    gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), chunk_clips=max(2048, n_shard // 8),
                                         device=dev, idx_base=lo)
     e2e_steps = max(3, min(args.steps, 10))
     h2d = gallery.nbytes + (Q * T * 512 * 2 if (rank == 0 or world == 1) else 0)

@@ -108,6 +108,19 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout,
                            const float* gscale_dev, const float* cscale_dev, float* scores_dev,
                            int64_t ld_g, int64_t ld_c, void* stream);
 
+/* Host-only planning step of K1 (no device, no ctx): how the clips of the column-side operand are
+ * packed into tiles of `width` (128 or 256) columns.  Whole clips are packed greedily; a clip
+ * longer than `width` is cut into `partial` tiles when allow_split (legal only when both pooling
+ * reductions are the same operation), otherwise JEGAL_ERR_UNSUPPORTED is returned with *n_out =
+ * the offending clip.  Bit j of endmask[c] marks column 32c+j as the last column of a clip.
+ * out may be NULL to query the count; at most max_out tiles are written. */
+typedef struct {
+  int32_t row0, n_valid, clip0, partial;
+  uint32_t endmask[8];
+} jegal_column_tile;
+int jegal_plan_column_tiles(const int32_t* cu_len_host, int32_t n_clips, int32_t width, int32_t allow_split,
+                            jegal_column_tile* out, int32_t max_out, int32_t* n_out);
+
 /* K2 — per-query top-k of a dense [n_q, n_g] fp32 score matrix (row stride ld).
  * Descending by score, ties broken towards the lower index; indices are
  * returned + idx_offset (the shard's first global clip).  1 <= k <= 32.

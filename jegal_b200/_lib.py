@@ -33,6 +33,7 @@ SYMBOLS = [
     "jegal_spot",
     "jegal_simpool_pairs",
     "jegal_group_softmax",
+    "jegal_plan_column_tiles",
     "jegal_exchange_create",
     "jegal_exchange_ipc_handle",
     "jegal_exchange_connect",
@@ -113,6 +114,8 @@ def load() -> C.CDLL:
         lib.jegal_exchange_destroy.argtypes = [vp]
         lib.jegal_exchange_destroy.restype = None
         lib.jegal_topk_exchange.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
+    if hasattr(lib, "jegal_plan_column_tiles"):
+        lib.jegal_plan_column_tiles.argtypes = [C.POINTER(i32), i32, i32, i32, vp, i32, C.POINTER(i32)]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("jegal_layout_clips",):

@@ -39,26 +39,18 @@ int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, in
   return make_box_tmap_impl(ctx, out, rows_dev, n_rows, op_dtype, kTileRows);
 }
 
-namespace {
-
-// Pack whole clips greedily into column tiles of `width` rows.  A clip longer
-// than `width` is cut into pieces (flagged partial) when the pooling allows it.
-int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_split,
-                 jegal_layout::CTileSet* set) {
-  set->width = width;
-  set->allow_split = allow_split;
-  set->any_partial = false;
-  set->host.clear();
-  const std::vector<int32_t>& cu = L->cu_host;
+int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_split,
+                      std::vector<CTile>* out, bool* any_partial, int32_t* bad_clip) {
+  out->clear();
+  *any_partial = false;
   int32_t i = 0;
-  while (i < L->n_clips) {
+  while (i < n_clips) {
     const int32_t len = cu[i + 1] - cu[i];
     if (len > width) {
-      if (!allow_split)
-        return set_err(ctx, JEGAL_ERR_UNSUPPORTED,
-                       "clip " + std::to_string(i) + " has " + std::to_string(len) +
-                           " rows on the column side; a max-then-mean pooling needs <= " +
-                           std::to_string(width));
+      if (!allow_split) {
+        *bad_clip = i;
+        return JEGAL_ERR_UNSUPPORTED;
+      }
       for (int32_t off = 0; off < len; off += width) {
         CTile t{};
         t.row0 = cu[i] + off;
@@ -67,8 +59,8 @@ int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_sp
         t.partial = 1;
         const int32_t e = t.n_valid - 1;
         t.endmask[e >> 5] |= 1u << (e & 31);
-        set->host.push_back(t);
-        set->any_partial = true;
+        out->push_back(t);
+        *any_partial = true;
       }
       ++i;
       continue;
@@ -77,7 +69,7 @@ int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_sp
     t.row0 = cu[i];
     t.clip0 = i;
     int32_t used = 0;
-    while (i < L->n_clips) {
+    while (i < n_clips) {
       const int32_t l = cu[i + 1] - cu[i];
       if (used + l > width) break;
       used += l;
@@ -86,8 +78,23 @@ int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_sp
       ++i;
     }
     t.n_valid = used;
-    set->host.push_back(t);
+    out->push_back(t);
   }
+  return JEGAL_OK;
+}
+
+namespace {
+
+int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_split,
+                 jegal_layout::CTileSet* set) {
+  set->width = width;
+  set->allow_split = allow_split;
+  int32_t bad = -1;
+  const int rc = plan_column_tiles(L->cu_host.data(), L->n_clips, width, allow_split, &set->host, &set->any_partial, &bad);
+  if (rc != JEGAL_OK)
+    return set_err(ctx, rc, "clip " + std::to_string(bad) + " has " +
+                                std::to_string(L->cu_host[bad + 1] - L->cu_host[bad]) +
+                                " rows on the column side; a max-then-mean pooling needs <= " + std::to_string(width));
   set->n = static_cast<int>(set->host.size());
   return JEGAL_OK;
 }
@@ -138,6 +145,26 @@ using namespace jegal;
 extern "C" {
 
 const char* jegal_version(void) { return "jegal_b200 0.1 (sm_100a)"; }
+
+int jegal_plan_column_tiles(const int32_t* cu_len_host, int32_t n_clips, int32_t width, int32_t allow_split,
+                            jegal_column_tile* out, int32_t max_out, int32_t* n_out) {
+  if (!cu_len_host || n_clips < 0 || width < 32 || width > 256 || (width & 31) || !n_out) return JEGAL_ERR_ARG;
+  std::vector<CTile> tiles;
+  bool any_partial = false;
+  int32_t bad = -1;
+  const int rc = plan_column_tiles(cu_len_host, n_clips, width, allow_split != 0, &tiles, &any_partial, &bad);
+  if (rc != JEGAL_OK) {
+    *n_out = bad;
+    return rc;
+  }
+  *n_out = static_cast<int32_t>(tiles.size());
+  if (out) {
+    static_assert(sizeof(jegal_column_tile) == sizeof(CTile), "public and internal tile layouts must agree");
+    const int32_t n = std::min<int32_t>(max_out, *n_out);
+    std::memcpy(out, tiles.data(), sizeof(CTile) * static_cast<size_t>(n));
+  }
+  return JEGAL_OK;
+}
 
 int jegal_ctx_create(int device, jegal_ctx** out) {
   if (!out) return JEGAL_ERR_ARG;

@@ -507,10 +507,10 @@ template <int kEpi>
 int launch_grouped(jegal_ctx* ctx, const GroupedMaps& maps, const GroupedParams& p, cudaStream_t stream) {
   auto kern = grouped_kernel<kEpi>;
   constexpr size_t smem = grouped_smem_bytes();
-  static bool configured = false;
-  if (!configured) {
+  constexpr uint32_t bit = 1u << (16 + kEpi);
+  if (!(ctx->smem_configured & bit)) {
     JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
+    ctx->smem_configured |= bit;
   }
   int grid = ctx->sm_count;
   if (p.n_items < grid) grid = p.n_items;

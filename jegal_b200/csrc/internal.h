@@ -55,6 +55,7 @@ struct jegal_ctx {
   std::string err;
   int64_t launches = 0;
   void* encode_tiled = nullptr;  // PFN_cuTensorMapEncodeTiled
+  uint32_t smem_configured = 0;  // bit per kernel instantiation whose max dynamic smem was raised on this device
 };
 
 struct jegal_layout {
@@ -111,5 +112,11 @@ int make_box_tmap_impl(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, i
                        int box_rows);
 int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, int64_t n_rows,
                       int op_dtype);
+
+// Pure host logic (unit-tested without a GPU): pack whole clips greedily into column tiles of
+// `width` rows; clips longer than `width` are cut into partial tiles when `allow_split`.
+// Returns JEGAL_OK, or JEGAL_ERR_UNSUPPORTED with *bad_clip set.
+int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_split,
+                      std::vector<CTile>* out, bool* any_partial, int32_t* bad_clip);
 
 }  // namespace jegal

@@ -25,7 +25,9 @@
 //     of tiles i+1 and i+2; stationary-tile k-blocks are released one by one during the
 //     last row tile of a unit so the next column tile's load overlaps too;
 //   - work is split over clusters by "row-tile steps" inside L2-sized phases of
-//     R so that all CTAs stream the same slice of R at the same time.
+//     R so that all CTAs stream the same slice of R at the same time;
+//   - ragged column tiles: the MMA N of a unit is roundup16(columns its clips occupy), so
+//     greedy whole-clip packing wastes no tensor time on the unused part of a 256-wide tile.
 #include <cstdio>
 
 #include "internal.h"
@@ -254,7 +256,10 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       int32_t ct, rt0, nrt;
       uint32_t rs = 0, rphase = 0, unit = 0;
       while (it.next(ct, rt0, nrt)) {
-        const int32_t c_row = __ldg(&p.ctiles[ct].row0) + static_cast<int32_t>(rank) * kTileRows;
+        // the MMA of this unit is only as wide as its clips (N = roundup16(n_valid)); in a CTA pair
+        // each CTA supplies N/2 rows of the column operand
+        const int32_t n_unit = (__ldg(&p.ctiles[ct].n_valid) + 15) & ~15;
+        const int32_t c_row = __ldg(&p.ctiles[ct].row0) + static_cast<int32_t>(rank) * (n_unit / kCG);
         for (int32_t t = 0; t < nrt; ++t) {
           const int32_t r_row = (rt0 + t) * UMMA_M + static_cast<int32_t>(rank) * kTileRows;
           for (int kb = 0; kb < NKB; ++kb) {
@@ -309,6 +314,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       const uint64_t descC0 = make_smem_desc_sw128(smC);
       const uint64_t descR0 = make_smem_desc_sw128(smR);
       while (it.next(ct, rt0, nrt)) {
+        const uint32_t n_unit = (static_cast<uint32_t>(__ldg(&p.ctiles[ct].n_valid)) + 15u) & ~15u;
+        const uint32_t idesc = (p.idesc & ~(0x3fu << 17)) | ((n_unit >> 3) << 17);  // N field of the descriptor
         for (int32_t t = 0; t < nrt; ++t, ++tile) {
           const uint32_t buf = tile & 1u;
           mbar_wait(t_empty(buf), ((tile >> 1) & 1u) ^ 1u);
@@ -323,7 +330,7 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               // +32 bytes (2 x 16 B) per 16-element K step inside the 128 B swizzle row
-              umma_f16<kCG>(d_tmem, dR + 2u * k, dC + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16<kCG>(d_tmem, dR + 2u * k, dC + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit<kCG>(r_empty(rs));
             if (t == nrt - 1) umma_commit<kCG>(c_empty(kb));
@@ -449,11 +456,11 @@ int launch_simpool_t(jegal_ctx* ctx, const CUtensorMap& tmR, const CUtensorMap& 
                      const SimpoolParams& p, cudaStream_t stream) {
   auto kern = simpool_kernel<kCG, kStagesDefault, kColOp, kRowOp>;
   constexpr size_t smem = simpool_smem_bytes<kCG, kStagesDefault>();
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  constexpr uint32_t bit = 1u << ((kCG - 1) * 4 + kColOp * 2 + kRowOp);
+  if (!(ctx->smem_configured & bit)) {
     JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-    configured = true;
+    ctx->smem_configured |= bit;
   }
   const int64_t steps = static_cast<int64_t>(p.n_ctiles) * p.n_rtiles;
   int nclusters = ctx->sm_count / kCG;

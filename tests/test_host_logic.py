@@ -114,3 +114,64 @@ def test_synth_structure_is_learnable():
         _, s0, e0 = cs.boundaries[i][w]
         hit += oracle.spot_decision(a, w, s0, e0)[2]
     assert hit >= 8
+
+
+# ----------------------------------------------------------------------------- K1 tile planner (host-only ABI call)
+def _plan(lengths, width, allow_split):
+    import ctypes as C
+    lib = _lib.load()
+    cu = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    n = C.c_int32()
+    rc = lib.jegal_plan_column_tiles(cu.ctypes.data_as(C.POINTER(C.c_int32)), len(lengths), width, int(allow_split), None, 0, C.byref(n))
+    if rc != 0:
+        return rc, n.value, None
+    buf = np.zeros((n.value, 12), dtype=np.uint32)
+    rc = lib.jegal_plan_column_tiles(cu.ctypes.data_as(C.POINTER(C.c_int32)), len(lengths), width, int(allow_split),
+                                     buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+    return rc, n.value, buf
+
+
+def _check_plan(lengths, width, allow_split):
+    rc, n, tiles = _plan(lengths, width, allow_split)
+    assert rc == 0
+    cu = np.concatenate([[0], np.cumsum(lengths)])
+    covered = np.zeros(cu[-1], dtype=np.int32)
+    next_clip = 0
+    for t in tiles:
+        row0, n_valid, clip0, partial = (int(x) for x in t[:4])
+        mask = t[4:]
+        assert 1 <= n_valid <= width
+        covered[row0:row0 + n_valid] += 1
+        ends = [c * 32 + j for c in range(8) for j in range(32) if (int(mask[c]) >> j) & 1]
+        assert ends and ends[-1] == n_valid - 1
+        if partial:
+            assert allow_split and len(ends) == 1 and lengths[clip0] > width
+            assert cu[clip0] <= row0 and row0 + n_valid <= cu[clip0 + 1]
+            if row0 + n_valid == cu[clip0 + 1]:
+                next_clip = clip0 + 1
+        else:
+            assert clip0 == next_clip and row0 == cu[clip0]
+            assert [row0 + e + 1 for e in ends] == list(cu[clip0 + 1: clip0 + 1 + len(ends)])  # whole clips, in order
+            next_clip = clip0 + len(ends)
+            if next_clip < len(lengths) and lengths[next_clip] <= width:
+                assert n_valid + lengths[next_clip] > width  # greedy: the next clip did not fit
+    assert next_clip == len(lengths) and (covered == 1).all()
+
+
+def test_column_tile_planner_properties():
+    rng = np.random.default_rng(0)
+    for width in (128, 256):
+        for _ in range(40):
+            n = int(rng.integers(1, 60))
+            lengths = rng.integers(1, width + 1, n)
+            _check_plan(lengths, width, False)
+            lengths = np.where(rng.random(n) < 0.2, rng.integers(width + 1, 3 * width, n), lengths)
+            _check_plan(lengths, width, True)
+        _check_plan([width] * 5, width, False)
+        _check_plan([1] * 700, width, False)
+        _check_plan([16] * 65536, width, False)
+
+
+def test_column_tile_planner_rejects_overlong_clip_without_split():
+    rc, bad, _ = _plan([10, 300, 20], 256, False)
+    assert rc == -4 and bad == 1  # JEGAL_ERR_UNSUPPORTED, offending clip index
