@@ -321,6 +321,7 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   p.n_rows_R = static_cast<int32_t>(LR->rows);
   p.rowinfo_R = LR->rowinfo_dev;
   p.uni_len_R = LR->uniform_len;
+  p.dense = (LR->uniform_len == 1 && LC->uniform_len == 1) ? 1 : 0;  // 1 x 1 tiles: all pooling modes coincide
   p.cu_R = LR->cu_dev;
   p.cu_C = LC->cu_dev;
   p.rscale = cols_are_gest ? cscale_dev : gscale_dev;

@@ -43,6 +43,7 @@ struct SimpoolParams {
   int64_t ld_r;
   int64_t ld_c;
   uint32_t idesc;
+  int32_t dense;  // 1: every clip on both sides is one row -> plain GEMM epilogue (no pooling)
 };
 
 enum Op : int { OP_SUM = 0, OP_MAX = 1 };

@@ -132,6 +132,21 @@ __device__ __forceinline__ void emit(float acc, int32_t cclip, bool col_partial,
   }
 }
 
+// One-row clips on BOTH sides (clip-level embeddings, evaluate_retrieval.py:38-48): nothing to pool,
+// this is a plain GEMM epilogue — every thread stores the cosines of its row for the chunk's columns.
+__device__ __forceinline__ void store_chunk_dense(const uint32_t (&v)[32], int32_t ncols, int32_t cclip,
+                                                  const RowCtx& rc, const SimpoolParams& p) {
+  if (rc.rclip < 0) return;
+  float* dst = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r + static_cast<int64_t>(cclip) * p.ld_c;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < ncols) {
+      const float sc = p.cscale ? __ldg(p.cscale + cclip + j) : 1.0f;
+      dst[static_cast<int64_t>(j) * p.ld_c] = __uint_as_float(v[j]) * rc.rscale * sc;
+    }
+  }
+}
+
 // Pool one 32-column chunk of this thread's row: `em` marks the columns that end a segment.
 // Works in 8-column sub-blocks: a sub-block whose only possible segment end is its last column is
 // a 4-instruction tree reduction; one with an interior end is split into runs with 8-wide masks.
@@ -187,7 +202,7 @@ __device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em,
   }
 }
 
-template <int kCG, int kStages, int kColOp, int kRowOp>
+template <int kCG, int kStages, int kColOp, int kRowOp, bool kDense = false>
 __global__ void __launch_bounds__(kThreads, 1)
 simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
                const SimpoolParams p) {
@@ -421,12 +436,20 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           tmem_ld_wait();
           if (ch + 1 < nchunks) tmem_ld_32x32(t_addr + (ch + 1) * 32, vb);
           else release();
-          pool_chunk<kColOp, kRowOp>(va, em_a, acc, cclip, col_partial, rc, p);
+          if constexpr (kDense) {
+            store_chunk_dense(va, n_valid - ch * 32, clip0 + ch * 32, rc, p);
+          } else {
+            pool_chunk<kColOp, kRowOp>(va, em_a, acc, cclip, col_partial, rc, p);
+          }
           if (ch + 1 < nchunks) {
             tmem_ld_wait();
             if (ch + 2 < nchunks) tmem_ld_32x32(t_addr + (ch + 2) * 32, va);
             else release();
-            pool_chunk<kColOp, kRowOp>(vb, em_b, acc, cclip, col_partial, rc, p);
+            if constexpr (kDense) {
+              store_chunk_dense(vb, n_valid - (ch + 1) * 32, clip0 + (ch + 1) * 32, rc, p);
+            } else {
+              pool_chunk<kColOp, kRowOp>(vb, em_b, acc, cclip, col_partial, rc, p);
+            }
           }
         }
       }
@@ -451,12 +474,12 @@ constexpr size_t simpool_smem_bytes() {
 
 constexpr int kStagesDefault = 6;
 
-template <int kCG, int kColOp, int kRowOp>
+template <int kCG, int kColOp, int kRowOp, bool kDense = false>
 int launch_simpool_t(jegal_ctx* ctx, const CUtensorMap& tmR, const CUtensorMap& tmC,
                      const SimpoolParams& p, cudaStream_t stream) {
-  auto kern = simpool_kernel<kCG, kStagesDefault, kColOp, kRowOp>;
+  auto kern = simpool_kernel<kCG, kStagesDefault, kColOp, kRowOp, kDense>;
   constexpr size_t smem = simpool_smem_bytes<kCG, kStagesDefault>();
-  constexpr uint32_t bit = 1u << ((kCG - 1) * 4 + kColOp * 2 + kRowOp);
+  constexpr uint32_t bit = kDense ? (1u << (8 + kCG)) : (1u << ((kCG - 1) * 4 + kColOp * 2 + kRowOp));
   if (!(ctx->smem_configured & bit)) {
     JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
@@ -485,6 +508,7 @@ int launch_simpool_t(jegal_ctx* ctx, const CUtensorMap& tmR, const CUtensorMap& 
 template <int kCG>
 int launch_simpool_cg(jegal_ctx* ctx, int col_op, int row_op, const CUtensorMap& tmR,
                       const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream) {
+  if (p.dense) return launch_simpool_t<kCG, OP_SUM, OP_SUM, true>(ctx, tmR, tmC, p, stream);
   if (col_op == OP_SUM && row_op == OP_SUM)
     return launch_simpool_t<kCG, OP_SUM, OP_SUM>(ctx, tmR, tmC, p, stream);
   if (col_op == OP_MAX && row_op == OP_SUM)

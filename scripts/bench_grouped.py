@@ -77,6 +77,14 @@ def main():
     s = ops.simpool_allpairs(g16, gl, c16, cl, "mean_mean")
     ms = timeit(lambda: (ops.rank_of_positive(s), ops.rank_of_positive(s.t())))
     print(json.dumps({"stage": "K2 rank_of_positive both directions (cfg2)", "ms": ms}))
+    # ---- clip-level cosine matrix (one-row clips: dense GEMM epilogue), 65536 x 1000 clip vectors
+    a = torch.nn.functional.normalize(torch.randn(65536, 512, device=dev), dim=-1).bfloat16()
+    b = torch.nn.functional.normalize(torch.randn(1000, 512, device=dev), dim=-1).bfloat16()
+    la, lb = ops.Layout.from_lengths([1] * 65536), ops.Layout.from_lengths([1] * 1000)
+    ms = timeit(lambda: ops.simpool_allpairs(a, la, b, lb, "mean_mean"))
+    byts = (65536 + 1000) * 1024 + 65536 * 1000 * 4
+    print(json.dumps({"stage": "K1 dense epilogue: 65536 x 1000 clip-level cosine matrix", "ms": ms,
+                      "GBps": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / hbm, "TFLOPs": 2.0 * 512 * 65536 * 1000 / ms / 1e9}))
     # ---- K2 top-k at cfg5 size
     x = torch.randn(1000, 65536, device=dev)
     ms = timeit(lambda: ops.topk(x, 10))

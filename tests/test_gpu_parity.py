@@ -394,3 +394,17 @@ def test_topk_exchange_single_rank(dev):
         v, i = ex.topk(x, idx_offset=5)
         rv, ri = ops.topk(x, 10, idx_offset=5)
         assert torch.equal(i, ri) and torch.equal(v, rv)
+
+
+def test_clip_level_similarity_matrix_at_scale(dev):
+    """One-row clips on both sides (the reference's literal get_similarity_matrix, at 6000 x 2500):
+    the dense-store epilogue against an fp32 matmul of the same normalised rows."""
+    from jegal_b200 import scoring
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((6000, 512)).astype(np.float32)
+    b = rng.standard_normal((2500, 512)).astype(np.float32)
+    s = scoring.get_similarity_matrix(a, b).numpy()
+    ref = oracle.get_similarity_matrix(a, b).numpy()
+    assert s.shape == (6000, 2500) and np.abs(s - ref).max() < TOL
+    s2 = scoring.get_similarity_matrix(list(a[:37]), list(b[:5])).numpy()  # list-of-vectors input, ragged tile edges
+    assert np.abs(s2 - ref[:37, :5]).max() < TOL
