@@ -189,7 +189,13 @@ int jegal_ctx_create(int device, jegal_ctx** out) {
   return JEGAL_OK;
 }
 
-void jegal_ctx_destroy(jegal_ctx* ctx) { delete ctx; }
+void jegal_ctx_destroy(jegal_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->topk_ws_val) cudaFree(ctx->topk_ws_val);
+  if (ctx->topk_ws_idx) cudaFree(ctx->topk_ws_idx);
+  if (ctx->topk_ws_ticket) cudaFree(ctx->topk_ws_ticket);
+  delete ctx;
+}
 
 const char* jegal_last_error(const jegal_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 

@@ -56,6 +56,11 @@ struct jegal_ctx {
   std::string err;
   int64_t launches = 0;
   void* encode_tiled = nullptr;  // PFN_cuTensorMapEncodeTiled
+  // K2 workspace for rows cut into column slices: per (row, slice) a 32-entry list + a ticket per row
+  float* topk_ws_val = nullptr;
+  int32_t* topk_ws_idx = nullptr;
+  uint32_t* topk_ws_ticket = nullptr;
+  size_t topk_ws_elems = 0, topk_ws_rows = 0;
   uint32_t smem_configured = 0;  // bit per kernel instantiation whose max dynamic smem was raised on this device
 };
 

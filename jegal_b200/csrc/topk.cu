@@ -5,6 +5,8 @@
 //
 // Ordering rule everywhere: descending score, ties towards the LOWER index, so a
 // gallery sharded over several GPUs merges to exactly the single-GPU list.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace jegal {
@@ -41,6 +43,21 @@ struct WarpList {
       }
     }
   }
+  // like offer(), with the current k-th item (tv, ti) cached by the caller: an empty vote costs one ballot
+  __device__ __forceinline__ void offer_cached(float cv, int32_t ci, bool valid, int k, int lane, float& tv, int32_t& ti) {
+    uint32_t m = __ballot_sync(0xffffffffu, valid && better(cv, ci, tv, ti));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float bv = __shfl_sync(0xffffffffu, cv, src);
+      const int32_t bi = __shfl_sync(0xffffffffu, ci, src);
+      if (better(bv, bi, tv, ti)) {
+        insert(bv, bi, lane);
+        tv = __shfl_sync(0xffffffffu, v, k - 1);
+        ti = __shfl_sync(0xffffffffu, i, k - 1);
+      }
+    }
+  }
   // offer one candidate per lane; candidates that beat the current k-th item get inserted
   __device__ __forceinline__ void offer(float cv, int32_t ci, bool valid, int k, int lane) {
     float tv = __shfl_sync(0xffffffffu, v, k - 1);
@@ -60,20 +77,29 @@ struct WarpList {
   }
 };
 
-// one block per query row
+// A query row is cut into gridDim.y column slices (16-byte aligned); block (q, s) streams slice s of
+// row q.  With more than one slice the block's list goes to a workspace and the LAST block of the
+// row to finish (atomic ticket) merges the slices — short serial chains per block and enough blocks
+// to keep HBM busy even for ~1000 rows on 148 SMs.
 __global__ void __launch_bounds__(kTopkWarps * 32)
 topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k, int32_t idx_offset,
-            float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+            float* __restrict__ out_val, int32_t* __restrict__ out_idx, float* __restrict__ ws_val,
+            int32_t* __restrict__ ws_idx, uint32_t* __restrict__ ws_ticket) {
   __shared__ float sv[kTopkWarps][32];
   __shared__ int32_t si[kTopkWarps][32];
+  __shared__ uint32_t s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = blockIdx.x;
+  const int32_t n_slices = gridDim.y, slice = blockIdx.y;
   const float* row = scores + q * ld;
   WarpList L;
   L.init();
   // vector body: needs a 16-byte aligned row start
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
-  const int32_t n4 = vec_ok ? (n_g >> 2) : 0;
+  const int32_t n4_all = vec_ok ? (n_g >> 2) : 0;
+  const int32_t per = (n4_all + n_slices - 1) / n_slices;
+  const int32_t lo4 = min(slice * per, n4_all);
+  const int32_t n4 = min(lo4 + per, n4_all);  // this block streams float4 indices [lo4, n4)
   const float4* row4 = reinterpret_cast<const float4*>(row);
   // kU independent 16-byte loads per lane per batch, and the NEXT batch is already in flight while
   // this one is examined (software pipelining); a whole batch is skipped with one vote when nothing
@@ -82,11 +108,11 @@ topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k
   constexpr int kStride = kTopkWarps * 32 * kU;
   const float4 kNegInf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   float4 x[kU], nx[kU];
-  int32_t base = warp * 32 * kU;
+  int32_t base = lo4 + warp * 32 * kU;
 #pragma unroll
   for (int u = 0; u < kU; ++u) {
     const int32_t j4 = base + u * 32 + lane;
-    nx[u] = (base < n4 && j4 < n4) ? __ldg(row4 + j4) : kNegInf4;
+    nx[u] = j4 < n4 ? __ldg(row4 + j4) : kNegInf4;
   }
   for (; base < n4; base += kStride) {
 #pragma unroll
@@ -97,7 +123,8 @@ topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k
       const int32_t j4 = nbase + u * 32 + lane;
       nx[u] = j4 < n4 ? __ldg(row4 + j4) : kNegInf4;
     }
-    const float tv = __shfl_sync(0xffffffffu, L.v, k - 1);
+    float tv = __shfl_sync(0xffffffffu, L.v, k - 1);
+    int32_t ti = __shfl_sync(0xffffffffu, L.i, k - 1);
     float mx = -INFINITY;
 #pragma unroll
     for (int u = 0; u < kU; ++u) mx = fmaxf(mx, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
@@ -109,28 +136,49 @@ topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k
       const int32_t j = j4 * 4;
       const float um = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
       if (!__any_sync(0xffffffffu, valid && um >= tv)) continue;
-      L.offer(x[u].x, j + 0, valid, k, lane);
-      L.offer(x[u].y, j + 1, valid, k, lane);
-      L.offer(x[u].z, j + 2, valid, k, lane);
-      L.offer(x[u].w, j + 3, valid, k, lane);
+      L.offer_cached(x[u].x, j + 0, valid, k, lane, tv, ti);
+      L.offer_cached(x[u].y, j + 1, valid, k, lane, tv, ti);
+      L.offer_cached(x[u].z, j + 2, valid, k, lane, tv, ti);
+      L.offer_cached(x[u].w, j + 3, valid, k, lane, tv, ti);
     }
   }
-  for (int32_t base = n4 * 4 + warp * 32; base < n_g; base += kTopkWarps * 32) {
-    const int32_t j = base + lane;
-    const bool valid = j < n_g;
-    const float x = valid ? __ldg(row + j) : 0.f;
-    L.offer(x, j, valid, k, lane);
+  if (slice == n_slices - 1) {  // scalar tail of the row (and unaligned rows)
+    for (int32_t b2 = n4_all * 4 + warp * 32; b2 < n_g; b2 += kTopkWarps * 32) {
+      const int32_t j = b2 + lane;
+      const bool valid = j < n_g;
+      const float xv = valid ? __ldg(row + j) : 0.f;
+      L.offer(xv, j, valid, k, lane);
+    }
   }
   sv[warp][lane] = L.v;
   si[warp][lane] = L.i;
   __syncthreads();
-  if (warp == 0) {
-    for (int w = 1; w < kTopkWarps; ++w) L.offer(sv[w][lane], si[w][lane], lane < k, k, lane);
-    if (lane < k) {
-      const bool real = L.i != 0x7fffffff;
-      out_val[q * k + lane] = L.v;
-      out_idx[q * k + lane] = real ? L.i + idx_offset : -1;
+  if (warp != 0) return;
+  for (int w = 1; w < kTopkWarps; ++w) L.offer(sv[w][lane], si[w][lane], lane < k, k, lane);
+  if (n_slices > 1) {
+    // publish this slice's list, take a ticket; the last slice of the row merges all of them
+    const int64_t wbase = (q * n_slices + slice) * 32;
+    ws_val[wbase + lane] = L.v;
+    ws_idx[wbase + lane] = L.i;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) s_last = atomicAdd(ws_ticket + q, 1u);
+    __syncwarp();
+    if (s_last != static_cast<uint32_t>(n_slices - 1)) return;
+    __threadfence();
+    for (int32_t s2 = 0; s2 < n_slices; ++s2) {
+      if (s2 == slice) continue;
+      const int64_t ob = (q * n_slices + s2) * 32;
+      const float cv = __ldcg(ws_val + ob + lane);
+      const int32_t ci = __ldcg(ws_idx + ob + lane);
+      L.offer(cv, ci, lane < k && ci != 0x7fffffff, k, lane);
     }
+    if (lane == 0) ws_ticket[q] = 0;  // ready for the next launch
+  }
+  if (lane < k) {
+    const bool real = L.i != 0x7fffffff;
+    out_val[q * k + lane] = L.v;
+    out_idx[q * k + lane] = real ? L.i + idx_offset : -1;
   }
 }
 
@@ -200,8 +248,33 @@ rank_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld_row, int64
 int launch_topk(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
                 int32_t idx_offset, float* out_val, int32_t* out_idx, cudaStream_t stream) {
   if (n_q <= 0) return JEGAL_OK;
-  topk_kernel<<<static_cast<unsigned>(n_q), kTopkWarps * 32, 0, stream>>>(scores, n_g, ld, k, idx_offset,
-                                                                        out_val, out_idx);
+  // rows are only sliced when there are too few of them to fill the GPU (every slice pays the start-up
+  // phase of an empty list again); at least 16 K floats per block
+  const int64_t capacity = static_cast<int64_t>(ctx->sm_count) * 8;
+  int64_t slices = capacity / n_q;
+  slices = std::min<int64_t>(slices, std::max<int64_t>(1, n_g / 16384));
+  slices = std::max<int64_t>(1, std::min<int64_t>(slices, 64));
+  if (slices > 1) {
+    const size_t need = static_cast<size_t>(n_q) * slices * 32;
+    if (ctx->topk_ws_elems < need || ctx->topk_ws_rows < static_cast<size_t>(n_q)) {
+      // one-time (re)allocation; stream-ordered use afterwards
+      JEGAL_CUDA_OK(ctx, cudaStreamSynchronize(stream));
+      if (ctx->topk_ws_val) cudaFree(ctx->topk_ws_val);
+      if (ctx->topk_ws_idx) cudaFree(ctx->topk_ws_idx);
+      if (ctx->topk_ws_ticket) cudaFree(ctx->topk_ws_ticket);
+      ctx->topk_ws_val = nullptr; ctx->topk_ws_idx = nullptr; ctx->topk_ws_ticket = nullptr;
+      ctx->topk_ws_elems = 0; ctx->topk_ws_rows = 0;
+      JEGAL_CUDA_OK(ctx, cudaMalloc(&ctx->topk_ws_val, need * sizeof(float)));
+      JEGAL_CUDA_OK(ctx, cudaMalloc(&ctx->topk_ws_idx, need * sizeof(int32_t)));
+      JEGAL_CUDA_OK(ctx, cudaMalloc(&ctx->topk_ws_ticket, static_cast<size_t>(n_q) * sizeof(uint32_t)));
+      JEGAL_CUDA_OK(ctx, cudaMemset(ctx->topk_ws_ticket, 0, static_cast<size_t>(n_q) * sizeof(uint32_t)));
+      ctx->topk_ws_elems = need;
+      ctx->topk_ws_rows = static_cast<size_t>(n_q);
+    }
+  }
+  const dim3 grid(static_cast<unsigned>(n_q), static_cast<unsigned>(slices));
+  topk_kernel<<<grid, kTopkWarps * 32, 0, stream>>>(scores, n_g, ld, k, idx_offset, out_val, out_idx, ctx->topk_ws_val,
+                                                   ctx->topk_ws_idx, ctx->topk_ws_ticket);
   JEGAL_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;
   return JEGAL_OK;

@@ -408,3 +408,14 @@ def test_clip_level_similarity_matrix_at_scale(dev):
     assert s.shape == (6000, 2500) and np.abs(s - ref).max() < TOL
     s2 = scoring.get_similarity_matrix(list(a[:37]), list(b[:5])).numpy()  # list-of-vectors input, ragged tile edges
     assert np.abs(s2 - ref[:37, :5]).max() < TOL
+
+
+def test_topk_few_rows_sliced(dev):
+    """Few query rows: K2 cuts every row into column slices merged by the last block of the row."""
+    from jegal_b200 import ops
+    for nq, ng in ((3, 300000), (17, 70001)):
+        x = torch.randint(0, 1000, (nq, ng), device=dev).float()
+        for _ in range(2):  # the ticket counters must be reusable
+            v, i = ops.topk(x, 10, idx_offset=3)
+            rv, ri = oracle.topk(x.cpu().numpy(), 10)
+            assert np.array_equal(i.cpu().numpy(), ri + 3) and np.array_equal(v.cpu().numpy(), rv)
