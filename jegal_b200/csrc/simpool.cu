@@ -123,7 +123,7 @@ __device__ __forceinline__ void emit(float acc, int32_t cclip, bool col_partial,
     const float val = v * sc;
     float* dst = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r + static_cast<int64_t>(cclip) * p.ld_c;
     if (rc.complete && !col_partial) {
-      *dst = val;
+      __stcs(dst, val);  // streaming store: the score matrix is written once and not re-read by this kernel
     } else if constexpr (kRowOp == OP_MAX) {
       atomic_max_f32(dst, val);
     } else {
@@ -266,7 +266,9 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       const uint64_t pol_R = policy_evict_last();    // R chunk is re-streamed by every unit
-      const uint64_t pol_C = policy_evict_normal();
+      // a column tile is fetched once per phase of R by exactly one cluster: no reuse inside a phase,
+      // so it must not displace the R chunk every cluster re-streams (c_policy: 0 normal, 1 last, 2 first)
+      const uint64_t pol_C = p.c_policy == 1 ? policy_evict_last() : p.c_policy == 2 ? policy_evict_first() : policy_evict_normal();
       UnitIter it(p, cluster, nclusters);
       int32_t ct, rt0, nrt;
       uint32_t rs = 0, rphase = 0, unit = 0;

@@ -419,3 +419,32 @@ def test_topk_few_rows_sliced(dev):
             v, i = ops.topk(x, 10, idx_offset=3)
             rv, ri = oracle.topk(x.cpu().numpy(), 10)
             assert np.array_equal(i.cpu().numpy(), ri + 3) and np.array_equal(v.cpu().numpy(), rv)
+
+
+def test_empty_and_degenerate_inputs(dev):
+    from jegal_b200 import ops, scoring
+    from jegal_b200._lib import JegalError
+    g = rand_clips(3, 5, 9, 70)
+    empty = ops.Layout.from_lengths([])
+    assert empty.n_clips == 0 and empty.rows == 0
+    z = torch.empty((0, 512), dtype=torch.bfloat16, device=dev)
+    gl = ops.Layout.from_lengths([len(x) for x in g])
+    g16, _ = ops.prep(torch.from_numpy(np.concatenate(g)).to(dev), gl)
+    s = ops.simpool_allpairs(g16, gl, z, empty, "max_t_mean_w")
+    assert tuple(s.shape) == (3, 0)
+    s = ops.simpool_allpairs(z, empty, g16, gl, "mean_mean")
+    assert tuple(s.shape) == (0, 3)
+    v, i = ops.topk(torch.empty((4, 0), dtype=torch.float32, device=dev), 5)
+    assert (i == -1).all() and torch.isinf(v).all()
+    with pytest.raises(JegalError):  # an empty clip is rejected when the layout is built
+        ops.Layout(np.array([0, 4, 4, 9], dtype=np.int32))
+    with pytest.raises(JegalError):  # rows do not match the layout
+        ops.prep(torch.zeros((5, 512), device=dev), gl)
+    with pytest.raises(JegalError):
+        ops.topk(torch.zeros((2, 8), device=dev), 33)
+    # constant (all-tie) scores: lowest indices win, in order
+    v, i = ops.topk(torch.ones((3, 1000), device=dev), 7)
+    assert (i.cpu().numpy() == np.arange(7)[None, :]).all()
+    # a single one-frame / one-word pair
+    one = scoring.score_allpairs([g[0][:1]], [g[1][:1]], "max_max")
+    assert abs(one[0, 0] - float(oracle.cos_tile(g[0][:1], g[1][:1]))) < TOL

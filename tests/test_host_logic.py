@@ -175,3 +175,14 @@ def test_column_tile_planner_properties():
 def test_column_tile_planner_rejects_overlong_clip_without_split():
     rc, bad, _ = _plan([10, 300, 20], 256, False)
     assert rc == -4 and bad == 1  # JEGAL_ERR_UNSUPPORTED, offending clip index
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_ctx_create_fails_cleanly_without_gpu():
+    import ctypes as C
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.jegal_ctx_create(0, C.byref(h))
+    assert rc == -2 and not h.value  # JEGAL_ERR_DEVICE, no context, no crash
+    assert lib.jegal_last_error(None) == b"null ctx"
+    assert lib.jegal_launch_count(None) == 0
