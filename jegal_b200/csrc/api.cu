@@ -263,7 +263,9 @@ int32_t jegal_layout_clips(const jegal_layout* L) { return L ? L->n_clips : 0; }
 int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype,
                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
                float* inv_meannorm_dev, void* mean_rows_dev, void* stream) {
-  if (!ctx || !layout || !emb_dev || !out_rows_dev) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
+  if (!ctx || !layout) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
+  if (layout->n_clips == 0) return JEGAL_OK;
+  if (!emb_dev || !out_rows_dev) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
   if ((reinterpret_cast<uintptr_t>(emb_dev) | reinterpret_cast<uintptr_t>(out_rows_dev)) & 15u)
     return set_err(ctx, JEGAL_ERR_ARG, "prep: buffers must be 16-byte aligned");
   return launch_prep(ctx, layout, emb_dev, in_dtype, normalize_rows, row_eps, mean_eps, out_dtype,
@@ -274,14 +276,15 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
                            const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
                            int pool_mode, const float* gscale_dev, const float* cscale_dev,
                            float* scores_dev, int64_t ld_g, int64_t ld_c, void* stream_) {
-  if (!ctx || !gest_layout || !cont_layout || !gest_rows_dev || !cont_rows_dev || !scores_dev)
-    return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: null argument");
+  if (!ctx || !gest_layout || !cont_layout) return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: null argument");
   if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16)
     return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: op_dtype must be JEGAL_BF16 or JEGAL_F16");
   const int32_t nG = gest_layout->n_clips, nC = cont_layout->n_clips;
+  if (nG == 0 || nC == 0) return JEGAL_OK;  // an empty side: empty score matrix, nothing to launch
+  if (!gest_rows_dev || !cont_rows_dev || !scores_dev)
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: null argument");
   if (!((ld_g == nC && ld_c == 1) || (ld_g == 1 && ld_c == nG)))
     return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: (ld_g, ld_c) must be (n_cont, 1) or (1, n_gest)");
-  if (nG == 0 || nC == 0) return JEGAL_OK;
   if ((reinterpret_cast<uintptr_t>(gest_rows_dev) | reinterpret_cast<uintptr_t>(cont_rows_dev)) & 15u)
     return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: operand rows must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -359,7 +362,8 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
 
 int jegal_topk(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
                int32_t idx_offset, float* topk_val_dev, int32_t* topk_idx_dev, void* stream) {
-  if (!ctx || !scores_dev || !topk_val_dev || !topk_idx_dev) return set_err(ctx, JEGAL_ERR_ARG, "topk: null argument");
+  if (!ctx || (!scores_dev && n_g > 0 && n_q > 0) || !topk_val_dev || !topk_idx_dev)
+    return set_err(ctx, JEGAL_ERR_ARG, "topk: null argument");
   if (k < 1 || k > 32) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "topk: k must be in [1, 32]");
   if (n_q < 0 || n_g < 0 || ld < n_g) return set_err(ctx, JEGAL_ERR_ARG, "topk: bad shape");
   return launch_topk(ctx, scores_dev, n_q, n_g, ld, k, idx_offset, topk_val_dev, topk_idx_dev,
