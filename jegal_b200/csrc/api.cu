@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -357,6 +358,32 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   if (rc != JEGAL_OK) return rc;
   rc = make_operand_tmap(ctx, &tmC, rowsC, LC->rows, op_dtype);
   if (rc != JEGAL_OK) return rc;
+  if (env_int("JEGAL_K1_TRACE", 0)) {  // debug: per-role cycle accounting, printed to stderr (synchronises)
+    const int ncta = ctx->sm_count;
+    unsigned long long* tbuf = nullptr;
+    JEGAL_CUDA_OK(ctx, cudaMalloc(&tbuf, sizeof(unsigned long long) * 16 * ncta));
+    JEGAL_CUDA_OK(ctx, cudaMemsetAsync(tbuf, 0, sizeof(unsigned long long) * 16 * ncta, stream));
+    p.trace = tbuf;
+    rc = launch_simpool(ctx, cg, col_op, row_op, tmR, tmC, p, stream);
+    JEGAL_CUDA_OK(ctx, cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> h(16 * ncta);
+    cudaMemcpy(h.data(), tbuf, sizeof(unsigned long long) * 16 * ncta, cudaMemcpyDeviceToHost);
+    cudaFree(tbuf);
+    double acc[16] = {0};
+    int n_lead = 0;
+    for (int b = 0; b < ncta; ++b)
+      if (h[16 * b + 7] > 0) { ++n_lead; for (int k = 0; k < 16; ++k) acc[k] += static_cast<double>(h[16 * b + k]); }
+    if (n_lead > 0) {
+      for (int k = 0; k < 16; ++k) acc[k] /= n_lead;
+      std::fprintf(stderr,
+                   "[K1 trace, mean cycles over %d leader CTAs] producer: wait r_empty %.0f, wait c_empty %.0f, total %.0f | "
+                   "mma: wait t_empty %.0f, wait c_full %.0f, wait r_full %.0f, total %.0f | "
+                   "epi0: wait t_full %.0f, pool %.0f, total %.0f, tiles %.0f | epi1: wait t_full %.0f, pool %.0f, total %.0f\n",
+                   n_lead, acc[0], acc[1], acc[2], acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10], acc[11], acc[12],
+                   acc[13], acc[14]);
+    }
+    return rc;
+  }
   return launch_simpool(ctx, cg, col_op, row_op, tmR, tmC, p, stream);
 }
 

@@ -97,6 +97,18 @@ struct UnitIter {
   }
 };
 
+// cycle accounting for JEGAL_K1_TRACE=1 (p.trace != nullptr): slot += cycles spent in `stmt`
+#define JEGAL_TRACED(slot, stmt)                         \
+  do {                                                   \
+    if (p.trace) {                                       \
+      const long long t0__ = clock64();                  \
+      stmt;                                              \
+      tr[slot] += static_cast<unsigned long long>(clock64() - t0__); \
+    } else {                                             \
+      stmt;                                              \
+    }                                                    \
+  } while (0)
+
 struct RowCtx {
   int32_t rclip;
   float rscale;
@@ -272,6 +284,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       UnitIter it(p, cluster, nclusters);
       int32_t ct, rt0, nrt;
       uint32_t rs = 0, rphase = 0, unit = 0;
+      unsigned long long tr[4] = {0, 0, 0, 0};
+      const long long t_begin = clock64();
       while (it.next(ct, rt0, nrt)) {
         // the MMA of this unit is only as wide as its clips (N = roundup16(n_valid)); in a CTA pair
         // each CTA supplies N/2 rows of the column operand
@@ -282,7 +296,7 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           for (int kb = 0; kb < NKB; ++kb) {
             if (t == 0) {
               // (re)load stationary k-block kb once the previous unit's MMAs released it
-              if (unit > 0) mbar_wait(c_empty(kb), (unit - 1) & 1u);
+              if (unit > 0) JEGAL_TRACED(1, mbar_wait(c_empty(kb), (unit - 1) & 1u));
               if constexpr (kCG == 2) {
                 if (rank == 0) mbar_arrive_expect_tx(c_full(kb), kTileBytes * 2);
                 tma_load_2d_pair(&tmC, c_full(kb) & kPeerBitMask, smC + kb * kTileBytes,
@@ -292,7 +306,7 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
                 tma_load_2d(&tmC, c_full(kb), smC + kb * kTileBytes, kb * kBlockK, c_row, pol_C);
               }
             }
-            mbar_wait(r_empty(rs), rphase ^ 1u);
+            JEGAL_TRACED(0, mbar_wait(r_empty(rs), rphase ^ 1u));
             if constexpr (kCG == 2) {
               if (rank == 0) mbar_arrive_expect_tx(r_full(rs), kTileBytes * 2);
               tma_load_2d_pair(&tmR, r_full(rs) & kPeerBitMask, smR + rs * kTileBytes, kb * kBlockK,
@@ -308,6 +322,10 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           }
         }
         ++unit;
+      }
+      if (p.trace) {
+        unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
+        g[0] = tr[0]; g[1] = tr[1]; g[2] = static_cast<unsigned long long>(clock64() - t_begin);
       }
       // producer tail: do not leave while tcgen05.commit arrivals may still be in
       // flight towards this CTA's barriers (the peer CTA of a pair must stay alive).
@@ -328,6 +346,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       UnitIter it(p, cluster, nclusters);
       int32_t ct, rt0, nrt;
       uint32_t rs = 0, rphase = 0, unit = 0, tile = 0;
+      unsigned long long tr[4] = {0, 0, 0, 0};
+      const long long t_begin = clock64();
       const uint64_t descC0 = make_smem_desc_sw128(smC);
       const uint64_t descR0 = make_smem_desc_sw128(smR);
       while (it.next(ct, rt0, nrt)) {
@@ -335,12 +355,12 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
         const uint32_t idesc = (p.idesc & ~(0x3fu << 17)) | ((n_unit >> 3) << 17);  // N field of the descriptor
         for (int32_t t = 0; t < nrt; ++t, ++tile) {
           const uint32_t buf = tile & 1u;
-          mbar_wait(t_empty(buf), ((tile >> 1) & 1u) ^ 1u);
+          JEGAL_TRACED(0, mbar_wait(t_empty(buf), ((tile >> 1) & 1u) ^ 1u));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * UMMA_N;
           for (int kb = 0; kb < NKB; ++kb) {
-            if (t == 0) mbar_wait(c_full(kb), unit & 1u);
-            mbar_wait(r_full(rs), rphase);
+            if (t == 0) JEGAL_TRACED(1, mbar_wait(c_full(kb), unit & 1u));
+            JEGAL_TRACED(2, mbar_wait(r_full(rs), rphase));
             tc_fence_after();
             const uint64_t dR = descR0 + static_cast<uint64_t>((rs * kTileBytes) >> 4);
             const uint64_t dC = descC0 + static_cast<uint64_t>((kb * kTileBytes) >> 4);
@@ -360,6 +380,10 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
         }
         ++unit;
       }
+      if (p.trace) {
+        unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
+        g[4] = tr[0]; g[5] = tr[1]; g[6] = tr[2]; g[7] = static_cast<unsigned long long>(clock64() - t_begin);
+      }
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue
@@ -369,6 +393,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
     UnitIter it(p, cluster, nclusters);
     int32_t ct, rt0, nrt;
     uint32_t tile = 0;
+    unsigned long long tr[4] = {0, 0, 0, 0};
+    const long long t_begin = clock64();
     while (it.next(ct, rt0, nrt)) {
       const CTile* ctile = p.ctiles + ct;
       const int32_t n_valid = __ldg(&ctile->n_valid);
@@ -421,8 +447,9 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           rc.complete = sb >= wrow0 && se <= wrow0 + 32;
         }
         const uint32_t buf = grp;
-        mbar_wait(t_full(buf), (tile >> 1) & 1u);
+        JEGAL_TRACED(0, mbar_wait(t_full(buf), (tile >> 1) & 1u));
         tc_fence_after();
+        const long long t_pool0 = p.trace ? clock64() : 0;
         const uint32_t t_addr = tmem_base + lane_off + buf * UMMA_N;
 
         // hand the TMEM buffer back to the MMA warp once its last chunk sits in registers
@@ -464,7 +491,12 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
             }
           }
         }
+        if (p.trace) tr[1] += static_cast<unsigned long long>(clock64() - t_pool0);
       }
+    }
+    if (p.trace && q == 0 && lane == 0) {
+      unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16 + 8 + grp * 4;
+      g[0] = tr[0]; g[1] = tr[1]; g[2] = static_cast<unsigned long long>(clock64() - t_begin); g[3] = tile;
     }
   }
 

@@ -37,6 +37,28 @@ ArrayLike = Union[np.ndarray, torch.Tensor, Sequence]
 _layout_cache: Dict[bytes, Layout] = {}
 
 
+class _Staging:
+    """One grow-only pinned host buffer for packing clip lists (cudaHostAlloc of gigabytes per call
+    costs more than the copy it speeds up).  Reuse waits for the previous H2D copy out of it."""
+
+    buf: Optional[torch.Tensor] = None
+    event: Optional[torch.cuda.Event] = None
+
+    @classmethod
+    def get(cls, nbytes: int) -> torch.Tensor:
+        if cls.event is not None:
+            cls.event.synchronize()
+        if cls.buf is None or cls.buf.numel() < nbytes:
+            cls.buf = None
+            cls.buf = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8, pin_memory=True)
+        return cls.buf[:nbytes]
+
+    @classmethod
+    def mark_copy(cls) -> None:
+        cls.event = torch.cuda.Event()
+        cls.event.record()
+
+
 def _device() -> torch.device:
     if not torch.cuda.is_available():
         raise JegalError("jegal_b200.scoring needs a CUDA (sm_100) device; there is no CPU path")
@@ -88,16 +110,21 @@ class PackedClips:
             dt = np.float16 if all(a.dtype == np.float16 for a in arrs) else np.float32
             host = None
         total = int(lengths.sum())
-        if arrs is not None:
-            buf = torch.empty((total, 512), dtype=torch.float16 if dt == np.float16 else torch.float32,
-                              pin_memory=pin and total > 0)
-            if total:
-                np.concatenate(arrs, axis=0, out=buf.numpy(), casting="same_kind")
+        tdt = torch.float16 if (dt if arrs is not None else host.dtype) == np.float16 else torch.float32
+        if total == 0:
+            return cls(torch.empty((0, 512), dtype=tdt, device=dev), layout_for(lengths))
+        if pin:
+            buf = _Staging.get(total * 512 * (2 if tdt == torch.float16 else 4)).view(tdt).view(total, 512)
         else:
-            buf = torch.from_numpy(np.ascontiguousarray(host))
-            if pin and total > 0:
-                buf = buf.pin_memory()
-        return cls(buf.to(dev, non_blocking=True), layout_for(lengths))
+            buf = torch.empty((total, 512), dtype=tdt)
+        if arrs is not None:
+            np.concatenate(arrs, axis=0, out=buf.numpy(), casting="same_kind")
+        else:
+            np.copyto(buf.numpy(), host, casting="same_kind")
+        rows = buf.to(dev, non_blocking=True)
+        if pin:
+            _Staging.mark_copy()
+        return cls(rows, layout_for(lengths))
 
     @classmethod
     def from_packed(cls, rows: torch.Tensor, cu_len: np.ndarray) -> "PackedClips":
