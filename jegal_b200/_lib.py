@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjegal_b200.so")
+# JEGAL_B200_LIB: developer override for A/B kernel builds (scripts/k1_variants.sh); never a fallback
+LIB_PATH = os.environ.get("JEGAL_B200_LIB") or os.path.join(_HERE, "libjegal_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # every symbol include/jegal_b200.h declares (tests check the .so exports all of them)

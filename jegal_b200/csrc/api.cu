@@ -195,6 +195,7 @@ void jegal_ctx_destroy(jegal_ctx* ctx) {
   if (ctx->topk_ws_val) cudaFree(ctx->topk_ws_val);
   if (ctx->topk_ws_idx) cudaFree(ctx->topk_ws_idx);
   if (ctx->topk_ws_ticket) cudaFree(ctx->topk_ws_ticket);
+  if (ctx->rowmat_ws) cudaFree(ctx->rowmat_ws);
   delete ctx;
 }
 
@@ -346,12 +347,64 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   p.idesc = ptx::make_idesc_f16(op_dtype == JEGAL_BF16 ? 1u : 0u, static_cast<uint32_t>(width),
                                 static_cast<uint32_t>(width));
 
+  // Two-pass mode.  The fused epilogue pays ~50 dependent instructions (segmented shuffles + an atomic) per
+  // column clip per tile; with many short column clips (word clips on the column side: ~12 per tile) it
+  // takes longer than the tile's MMAs (measured: 57 % of tensor peak on config 2, max_w_mean_t).  There K1
+  // only pools along columns and stores the per-row values as M[column clip][row] (one coalesced 128-byte
+  // store per warp and clip), and launch_rowreduce finishes over rows: 2 x rows x n_col_clips x 4 bytes of
+  // extra HBM traffic, no atomics, no output initialisation, bitwise reproducible.
+  // JEGAL_ROWMAT: -1 auto (default), 0 never, 1 always; JEGAL_ROWMAT_MAX_MB bounds the workspace (default 1024).
+  const int64_t ldm = (LR->rows + 31) & ~static_cast<int64_t>(31);
+  const int64_t ws_elems = ldm * LC->n_clips;
+  bool two_pass = false;
+  {
+    const int mode = env_int("JEGAL_ROWMAT", -1);
+    const int64_t max_bytes = static_cast<int64_t>(env_int("JEGAL_ROWMAT_MAX_MB", 1024)) << 20;
+    const bool fits = ws_elems * 4 <= max_bytes && ldm < (1ll << 31) && !cts->any_partial && !p.dense;
+    // auto: column clips shorter than 48 rows on average (>= ~5.3 segments per 256-column tile)
+    const bool many_short = LC->rows < static_cast<int64_t>(48) * LC->n_clips;
+    two_pass = fits && (mode == 1 || (mode < 0 && many_short));
+  }
+  if (two_pass) {
+    if (ctx->rowmat_ws_elems < static_cast<size_t>(ws_elems)) {
+      if (ctx->rowmat_ws) {
+        JEGAL_CUDA_OK(ctx, cudaStreamSynchronize(stream));
+        cudaFree(ctx->rowmat_ws);
+        ctx->rowmat_ws = nullptr;
+        ctx->rowmat_ws_elems = 0;
+      }
+      if (cudaMalloc(&ctx->rowmat_ws, static_cast<size_t>(ws_elems) * 4) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->rowmat_ws = nullptr;
+        two_pass = false;  // not enough device memory for the workspace: fused single pass
+      } else {
+        ctx->rowmat_ws_elems = static_cast<size_t>(ws_elems);
+      }
+    }
+  }
+  const int final_row_op = row_op;
+  if (two_pass) {
+    p.out = ctx->rowmat_ws;
+    p.ld_r = 1;
+    p.ld_c = ldm;
+    p.rscale = nullptr;
+    p.cscale = nullptr;
+    row_op = OP_NONE;
+  }
+
   // Results of clips that straddle warps / row tiles / column tiles are combined
   // with atomics and need an initialised output.
-  if (!LR->warp_aligned || cts->any_partial) {
+  if (!two_pass && (!LR->warp_aligned || cts->any_partial)) {
     rc = launch_fill_f32(ctx, scores_dev, static_cast<int64_t>(nG) * nC, row_op == OP_MAX ? -INFINITY : 0.0f, stream);
     if (rc != JEGAL_OK) return rc;
   }
+  auto finish = [&]() -> int {
+    if (!two_pass) return JEGAL_OK;
+    return launch_rowreduce(ctx, ctx->rowmat_ws, ldm, LR->cu_dev, LR->n_clips, LC->cu_dev, LC->n_clips, final_row_op,
+                            col_op == OP_SUM, cols_are_gest ? cscale_dev : gscale_dev,
+                            cols_are_gest ? gscale_dev : cscale_dev, scores_dev, cols_are_gest ? ld_c : ld_g,
+                            cols_are_gest ? ld_g : ld_c, stream);
+  };
 
   CUtensorMap tmR, tmC;
   rc = make_operand_tmap(ctx, &tmR, rowsR, LR->rows, op_dtype);
@@ -376,15 +429,16 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
     if (n_lead > 0) {
       for (int k = 0; k < 16; ++k) acc[k] /= n_lead;
       std::fprintf(stderr,
-                   "[K1 trace, mean cycles over %d leader CTAs] producer: wait r_empty %.0f, wait c_empty %.0f, total %.0f | "
+                   "%s[K1 trace, mean cycles over %d leader CTAs] producer: wait r_empty %.0f, wait c_empty %.0f, total %.0f | "
                    "mma: wait t_empty %.0f, wait c_full %.0f, wait r_full %.0f, total %.0f | "
                    "epi0: wait t_full %.0f, pool %.0f, total %.0f, tiles %.0f | epi1: wait t_full %.0f, pool %.0f, total %.0f\n",
-                   n_lead, acc[0], acc[1], acc[2], acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10], acc[11], acc[12],
+                   two_pass ? "(two-pass) " : "", n_lead, acc[0], acc[1], acc[2], acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10], acc[11], acc[12],
                    acc[13], acc[14]);
     }
-    return rc;
+    return rc != JEGAL_OK ? rc : finish();
   }
-  return launch_simpool(ctx, cg, col_op, row_op, tmR, tmC, p, stream);
+  rc = launch_simpool(ctx, cg, col_op, row_op, tmR, tmC, p, stream);
+  return rc != JEGAL_OK ? rc : finish();
 }
 
 int jegal_topk(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,

@@ -48,7 +48,9 @@ struct SimpoolParams {
   int32_t dense;  // 1: every clip on both sides is one row -> plain GEMM epilogue (no pooling)
 };
 
-enum Op : int { OP_SUM = 0, OP_MAX = 1 };
+// OP_NONE (row side only): no reduction over rows in K1 -- the per-row values go to a workspace matrix
+// and launch_rowreduce finishes the pooling (two-pass mode for column sides made of many short clips).
+enum Op : int { OP_SUM = 0, OP_MAX = 1, OP_NONE = 2 };
 
 }  // namespace jegal
 
@@ -63,6 +65,8 @@ struct jegal_ctx {
   int32_t* topk_ws_idx = nullptr;
   uint32_t* topk_ws_ticket = nullptr;
   size_t topk_ws_elems = 0, topk_ws_rows = 0;
+  float* rowmat_ws = nullptr;  // two-pass K1 workspace [n column clips][row stride] fp32, grown on demand
+  size_t rowmat_ws_elems = 0;
   uint32_t smem_configured = 0;  // bit per kernel instantiation whose max dynamic smem was raised on this device
 };
 
@@ -101,6 +105,11 @@ int set_err(jegal_ctx* ctx, int code, const std::string& msg);
 // host-side launchers implemented in the kernel files
 int launch_simpool(jegal_ctx* ctx, int cta_group, int col_op, int row_op, const CUtensorMap& tmR,
                    const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream);
+// pass 2 of the two-pass mode: out[r * ld_r + c * ld_c] = rscale[r] * cscale[c] * ROWOP_{row in clip r} M[c * ldm + row]
+// (mean: the sum is divided by the clip's rows; col_mean: also by the column clip's rows)
+int launch_rowreduce(jegal_ctx* ctx, const float* M, int64_t ldm, const int32_t* cu_R, int32_t n_rclips,
+                     const int32_t* cu_C, int32_t n_cclips, int row_op, bool col_mean, const float* rscale,
+                     const float* cscale, float* out, int64_t ld_r, int64_t ld_c, cudaStream_t stream);
 int launch_fill_f32(jegal_ctx* ctx, float* dst, int64_t n, float value, cudaStream_t stream);
 int launch_rowinfo(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,
                    int4* rowinfo_dev, cudaStream_t stream);

@@ -289,5 +289,21 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
   }
 }
 
+// Explicit global-space forms (a generic-address atomicAdd inside a non-inlined function drags in
+// the shared/local address-space dispatch).
+__device__ __forceinline__ void st_global_cs_f32(float* addr, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_global_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_global_max_f32(float* addr, float v) {
+  if (v >= 0.0f) {
+    asm volatile("red.global.max.s32 [%0], %1;" ::"l"(addr), "r"(__float_as_int(v)) : "memory");
+  } else {
+    asm volatile("red.global.min.u32 [%0], %1;" ::"l"(addr), "r"(__float_as_uint(v)) : "memory");
+  }
+}
+
 }  // namespace ptx
 }  // namespace jegal

@@ -50,6 +50,7 @@ __device__ __forceinline__ float op_ident() {
 }
 template <int kOp>
 __device__ __forceinline__ float op_apply(float a, float b) {
+  static_assert(kOp == OP_MAX || kOp == OP_SUM, "OP_NONE has no combine step");
   return kOp == OP_MAX ? fmaxf(a, b) : a + b;
 }
 
@@ -109,47 +110,76 @@ struct UnitIter {
     }                                                    \
   } while (0)
 
+// Per-thread row context of one tile.  flags: bit k (k < 5): lane + 2^k is in the same row segment;
+// kRcHead: first lane of its segment within the warp; kRcDirect: the whole clip lies inside this warp's
+// 32 rows and the column tile is not a piece of a split clip (plain store instead of an atomic);
+// kRcValid: the row exists.
 struct RowCtx {
   int32_t rclip;
   float rscale;
-  uint32_t same;  // bit k: lane + 2^k is in the same row segment
-  bool head;      // first lane of its segment within the warp
-  bool complete;  // the whole clip lies inside this warp's 32 rows
+  uint32_t flags;
+  float* out_row;  // p.out + rclip * ld_r
 };
+constexpr uint32_t kRcHead = 1u << 5, kRcDirect = 1u << 6, kRcValid = 1u << 7;
 
+// Reduce one pooled column-clip value over the rows of each row segment and write / combine it.
+// Deliberately NOT inlined: there are ~40 emit sites in the unrolled pooling code and the epilogue
+// was instruction-fetch bound (ncu: stall_no_inst + branch_resolving = 37 % of its samples with
+// the body inlined, 7.7 k SASS instructions = 123 KB against a 32 KB L1.5 instruction cache).
+#ifndef JEGAL_EMIT_INLINE
+#define JEGAL_EMIT_ATTR __noinline__
+#else
+#define JEGAL_EMIT_ATTR __forceinline__
+#endif
 template <int kColOp, int kRowOp>
-__device__ __forceinline__ void emit(float acc, int32_t cclip, bool col_partial, const RowCtx& rc,
-                                     const SimpoolParams& p) {
-  float v = rc.rclip >= 0 ? acc * rc.rscale : op_ident<kRowOp>();
+__device__ JEGAL_EMIT_ATTR void emit(float acc, int32_t cclip, float rscale, uint32_t flags, float* out_row,
+                                  const float* __restrict__ cscale, const int32_t* __restrict__ cu_C,
+                                  int32_t ld_c) {
+  // (an integer REDUX for warps that lie inside one clip was measured: no gain, the shuffles are not the limit)
+  float v = (flags & kRcValid) ? acc * rscale : op_ident<kRowOp>();
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const float o = __shfl_down_sync(0xffffffffu, v, 1u << k);
-    if ((rc.same >> k) & 1u) v = op_apply<kRowOp>(v, o);
+    if ((flags >> k) & 1u) v = op_apply<kRowOp>(v, o);
   }
-  if (rc.head) {
-    float sc = p.cscale ? __ldg(p.cscale + cclip) : 1.0f;
+  if (flags & kRcHead) {
+    float sc = cscale ? __ldg(cscale + cclip) : 1.0f;
     if constexpr (kColOp == OP_SUM) {
-      const int32_t len = __ldg(p.cu_C + cclip + 1) - __ldg(p.cu_C + cclip);
+      const int32_t len = __ldg(cu_C + cclip + 1) - __ldg(cu_C + cclip);
       sc *= 1.0f / static_cast<float>(len);
     }
     const float val = v * sc;
-    float* dst = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r + static_cast<int64_t>(cclip) * p.ld_c;
-    if (rc.complete && !col_partial) {
-      __stcs(dst, val);  // streaming store: the score matrix is written once and not re-read by this kernel
+    float* dst = out_row + static_cast<int64_t>(cclip) * ld_c;
+    if (flags & kRcDirect) {
+      st_global_cs_f32(dst, val);  // streaming store: the score matrix is written once, never re-read here
     } else if constexpr (kRowOp == OP_MAX) {
-      atomic_max_f32(dst, val);
+      red_global_max_f32(dst, val);
     } else {
-      atomicAdd(dst, val);
+      red_global_add_f32(dst, val);
     }
   }
 }
+// Two-pass mode (kRowOp == OP_NONE): no reduction over rows here.  The value goes to M[cclip][row] --
+// consecutive lanes are consecutive rows, so a warp writes one 128-byte line per column clip -- and
+// launch_rowreduce finishes the pooling.  m_ptr walks down M one column clip per emit (every emit is
+// followed by ++cclip), so a segment costs a predicated store and a 64-bit add instead of ~50 instructions.
+#define JEGAL_EMIT()                                                                                   \
+  do {                                                                                                 \
+    if constexpr (kRowOp == OP_NONE) {                                                                 \
+      if (rc.flags & kRcValid) st_global_cs_f32(m_ptr, acc);                                           \
+      m_ptr += p.ld_c;                                                                                 \
+    } else {                                                                                           \
+      emit<kColOp, kRowOp>(acc, cclip, rc.rscale, rc.flags, rc.out_row, p.cscale, p.cu_C,              \
+                           static_cast<int32_t>(p.ld_c));                                              \
+    }                                                                                                  \
+  } while (0)
 
 // One-row clips on BOTH sides (clip-level embeddings, evaluate_retrieval.py:38-48): nothing to pool,
 // this is a plain GEMM epilogue — every thread stores the cosines of its row for the chunk's columns.
 __device__ __forceinline__ void store_chunk_dense(const uint32_t (&v)[32], int32_t ncols, int32_t cclip,
                                                   const RowCtx& rc, const SimpoolParams& p) {
-  if (rc.rclip < 0) return;
-  float* dst = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r + static_cast<int64_t>(cclip) * p.ld_c;
+  if (!(rc.flags & kRcValid)) return;
+  float* dst = rc.out_row + static_cast<int64_t>(cclip) * p.ld_c;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j < ncols) {
@@ -159,20 +189,47 @@ __device__ __forceinline__ void store_chunk_dense(const uint32_t (&v)[32], int32
   }
 }
 
-// Pool one 32-column chunk of this thread's row: `em` marks the columns that end a segment.
-// Works in 8-column sub-blocks: a sub-block whose only possible segment end is its last column is
-// a 4-instruction tree reduction; one with an interior end is split into runs with 8-wide masks.
-// All branches are warp-uniform (every row of the tile sees the same column segmentation).
+template <int kOp>
+__device__ __forceinline__ float op3(float a, float b, float c) {
+  if constexpr (kOp == OP_MAX) return fmax3(a, b, c);
+  return (a + b) + c;
+}
+
+// An 8-column sub-block with exactly one interior segment end after column e (0..6):
+// lo = columns 0..e, hi = columns e+1..7.  e is warp-uniform, so this is one uniform jump into a
+// 2-4 instruction case (the generic run loop costs ~30 instructions per run).
+template <int kOp>
+__device__ __forceinline__ void split8(const uint32_t* v, uint32_t e, float& lo, float& hi) {
+  const float x0 = __uint_as_float(v[0]), x1 = __uint_as_float(v[1]), x2 = __uint_as_float(v[2]),
+              x3 = __uint_as_float(v[3]), x4 = __uint_as_float(v[4]), x5 = __uint_as_float(v[5]),
+              x6 = __uint_as_float(v[6]), x7 = __uint_as_float(v[7]);
+  switch (e) {
+    case 0: lo = x0; hi = op3<kOp>(x1, op3<kOp>(x2, x3, x4), op3<kOp>(x5, x6, x7)); break;
+    case 1: lo = op_apply<kOp>(x0, x1); hi = op3<kOp>(op3<kOp>(x2, x3, x4), op_apply<kOp>(x5, x6), x7); break;
+    case 2: lo = op3<kOp>(x0, x1, x2); hi = op3<kOp>(op3<kOp>(x3, x4, x5), x6, x7); break;
+    case 3: lo = op_apply<kOp>(op_apply<kOp>(x0, x1), op_apply<kOp>(x2, x3));
+            hi = op_apply<kOp>(op_apply<kOp>(x4, x5), op_apply<kOp>(x6, x7)); break;
+    case 4: lo = op3<kOp>(op3<kOp>(x0, x1, x2), x3, x4); hi = op3<kOp>(x5, x6, x7); break;
+    case 5: lo = op3<kOp>(op3<kOp>(x0, x1, x2), op_apply<kOp>(x3, x4), x5); hi = op_apply<kOp>(x6, x7); break;
+    default: lo = op3<kOp>(x0, op3<kOp>(x1, x2, x3), op3<kOp>(x4, x5, x6)); hi = x7; break;
+  }
+}
+
+// Pool one 32-column chunk of this thread's row: `em` marks the columns that end a segment and is
+// warp-uniform BY CONSTRUCTION (the caller rebuilds it with a ballot, so the compiler keeps it in
+// uniform registers and every branch below is a uniform branch without BSSY/BSYNC pairs).
+// Works in 8-column sub-blocks: no interior end -> a 4-instruction tree; one interior end -> split8;
+// two or more (clips shorter than 8 columns) -> runs with 8-wide masks.
 template <int kColOp, int kRowOp>
 __device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em, float& acc, int32_t& cclip,
-                                           bool col_partial, const RowCtx& rc, const SimpoolParams& p) {
+                                           float*& m_ptr, const RowCtx& rc, const SimpoolParams& p) {
   if ((em & 0x7f7f7f7fu) == 0u) {
     // whole chunk on the fast path (config 5: every chunk): no per-sub-block tests
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
       if ((em >> (8 * j + 7)) & 1u) {
-        emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+        JEGAL_EMIT();
         ++cclip;
         acc = op_ident<kColOp>();
       }
@@ -182,15 +239,18 @@ __device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em,
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t em8 = (em >> (8 * j)) & 0xffu;
-    if ((em8 & 0x7fu) == 0u) {
+    const uint32_t inner = em8 & 0x7fu;
+    if (inner == 0u) {
       acc = op_apply<kColOp>(acc, reduce8<kColOp>(v + 8 * j));
-      if (em8 & 0x80u) {
-        emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
-        ++cclip;
-        acc = op_ident<kColOp>();
-      }
+    } else if ((inner & (inner - 1u)) == 0u) {
+      float lo, hi;
+      split8<kColOp>(v + 8 * j, static_cast<uint32_t>(__ffs(inner) - 1), lo, hi);
+      acc = op_apply<kColOp>(acc, lo);
+      JEGAL_EMIT();
+      ++cclip;
+      acc = hi;
     } else {
-      uint32_t rem = em8;
+      uint32_t rem = inner;
       uint32_t start = 0;
       while (true) {
         const uint32_t e = rem ? static_cast<uint32_t>(__ffs(rem) - 1) : 7u;
@@ -203,13 +263,17 @@ __device__ __forceinline__ void pool_chunk(const uint32_t (&v)[32], uint32_t em,
         }
         acc = op_apply<kColOp>(acc, r);
         if (!rem) break;
-        emit<kColOp, kRowOp>(acc, cclip, col_partial, rc, p);
+        JEGAL_EMIT();
         ++cclip;
         acc = op_ident<kColOp>();
         rem &= rem - 1u;
         start = e + 1u;
-        if (start >= 8u) break;
       }
+    }
+    if (em8 & 0x80u) {
+      JEGAL_EMIT();
+      ++cclip;
+      acc = op_ident<kColOp>();
     }
   }
 }
@@ -410,7 +474,13 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
         // thread's row was requested while the previous own tile was being pooled (software
         // pipelining: the L2 round trip was 23 % of the epilogue's time when issued here).
         RowCtx rc;
-        {
+        if constexpr (kRowOp == OP_NONE) {
+          const int32_t row = (rt0 + t) * UMMA_M + static_cast<int32_t>(rank) * kTileRows + q * 32 + lane;
+          rc.rclip = row;
+          rc.rscale = 1.0f;
+          rc.flags = row < p.n_rows_R ? kRcValid : 0u;
+          rc.out_row = p.out + row;
+        } else {
           const int32_t row = (rt0 + t) * UMMA_M + static_cast<int32_t>(rank) * kTileRows + q * 32 + lane;
           int32_t sb = 0, se = 1;
           rc.rclip = -1;
@@ -435,16 +505,18 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           float rs_ = (rc.rclip >= 0 && p.rscale) ? __ldg(p.rscale + rc.rclip) : 1.0f;
           if constexpr (kRowOp == OP_SUM) rs_ *= 1.0f / static_cast<float>(se - sb);
           rc.rscale = rs_;
-          rc.same = 0;
+          uint32_t fl = rc.rclip >= 0 ? kRcValid : 0u;
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
             const int32_t o = __shfl_down_sync(0xffffffffu, rc.rclip, 1u << k);
-            if (lane + (1 << k) < 32 && o == rc.rclip) rc.same |= 1u << k;
+            if (lane + (1 << k) < 32 && o == rc.rclip) fl |= 1u << k;
           }
           const int32_t prev = __shfl_up_sync(0xffffffffu, rc.rclip, 1);
-          rc.head = rc.rclip >= 0 && (lane == 0 || prev != rc.rclip);
+          if (rc.rclip >= 0 && (lane == 0 || prev != rc.rclip)) fl |= kRcHead;
           const int32_t wrow0 = row - lane;
-          rc.complete = sb >= wrow0 && se <= wrow0 + 32;
+          if (sb >= wrow0 && se <= wrow0 + 32 && !col_partial) fl |= kRcDirect;
+          rc.flags = fl;
+          rc.out_row = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r;
         }
         const uint32_t buf = grp;
         JEGAL_TRACED(0, mbar_wait(t_full(buf), (tile >> 1) & 1u));
@@ -467,18 +539,20 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
 
         float acc = op_ident<kColOp>();
         int32_t cclip = clip0;
+        float* m_ptr = rc.out_row + static_cast<int64_t>(clip0) * p.ld_c;  // two-pass mode: &M[clip0][row]
         uint32_t va[32], vb[32];  // two chunks in flight: load c+1 while chunk c is pooled
         tmem_ld_32x32(t_addr, va);
         for (int ch = 0; ch < nchunks; ch += 2) {
-          const uint32_t em_a = __shfl_sync(0xffffffffu, my_em, ch);
-          const uint32_t em_b = __shfl_sync(0xffffffffu, my_em, ch + 1);
+          // every lane holds the same end mask; the ballot tells the compiler so (uniform registers)
+          const uint32_t em_a = __ballot_sync(0xffffffffu, (__shfl_sync(0xffffffffu, my_em, ch) >> lane) & 1u);
+          const uint32_t em_b = __ballot_sync(0xffffffffu, (__shfl_sync(0xffffffffu, my_em, ch + 1) >> lane) & 1u);
           tmem_ld_wait();
           if (ch + 1 < nchunks) tmem_ld_32x32(t_addr + (ch + 1) * 32, vb);
           else release();
           if constexpr (kDense) {
             store_chunk_dense(va, n_valid - ch * 32, clip0 + ch * 32, rc, p);
           } else {
-            pool_chunk<kColOp, kRowOp>(va, em_a, acc, cclip, col_partial, rc, p);
+            pool_chunk<kColOp, kRowOp>(va, em_a, acc, cclip, m_ptr, rc, p);
           }
           if (ch + 1 < nchunks) {
             tmem_ld_wait();
@@ -487,7 +561,7 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
             if constexpr (kDense) {
               store_chunk_dense(vb, n_valid - (ch + 1) * 32, clip0 + (ch + 1) * 32, rc, p);
             } else {
-              pool_chunk<kColOp, kRowOp>(vb, em_b, acc, cclip, col_partial, rc, p);
+              pool_chunk<kColOp, kRowOp>(vb, em_b, acc, cclip, m_ptr, rc, p);
             }
           }
         }
@@ -523,7 +597,7 @@ int launch_simpool_t(jegal_ctx* ctx, const CUtensorMap& tmR, const CUtensorMap& 
                      const SimpoolParams& p, cudaStream_t stream) {
   auto kern = simpool_kernel<kCG, kStagesDefault, kColOp, kRowOp, kDense>;
   constexpr size_t smem = simpool_smem_bytes<kCG, kStagesDefault>();
-  constexpr uint32_t bit = kDense ? (1u << (8 + kCG)) : (1u << ((kCG - 1) * 4 + kColOp * 2 + kRowOp));
+  constexpr uint32_t bit = 1u << ((kCG - 1) * 8 + (kDense ? 7 : kColOp * 3 + kRowOp));
   if (!(ctx->smem_configured & bit)) {
     JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
@@ -559,6 +633,10 @@ int launch_simpool_cg(jegal_ctx* ctx, int col_op, int row_op, const CUtensorMap&
     return launch_simpool_t<kCG, OP_MAX, OP_SUM>(ctx, tmR, tmC, p, stream);
   if (col_op == OP_MAX && row_op == OP_MAX)
     return launch_simpool_t<kCG, OP_MAX, OP_MAX>(ctx, tmR, tmC, p, stream);
+  if (col_op == OP_MAX && row_op == OP_NONE)
+    return launch_simpool_t<kCG, OP_MAX, OP_NONE>(ctx, tmR, tmC, p, stream);
+  if (col_op == OP_SUM && row_op == OP_NONE)
+    return launch_simpool_t<kCG, OP_SUM, OP_NONE>(ctx, tmR, tmC, p, stream);
   return set_err(ctx, JEGAL_ERR_ARG, "simpool: unsupported (col_op,row_op)");
 }
 
@@ -572,7 +650,71 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float value)
   for (int64_t i = (n4 << 2) + i0; i < n; i += stride) dst[i] = value;
 }
 
+// Pass 2 of the two-pass mode.  One warp per (row clip, kRrCols consecutive column clips): the lanes
+// stride over the clip's rows of M[c] (contiguous, coalesced; kRrCols independent streams in flight), a
+// butterfly finishes each reduction, lanes 0..kRrCols-1 write the scores.  The 8 warps of a block take
+// 8 * kRrCols consecutive column clips of one row clip.
+constexpr int kRrCols = 4;
+template <int kRowOp>
+__global__ void __launch_bounds__(256)
+rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __restrict__ cu_R, int32_t n_rclips,
+                 const int32_t* __restrict__ cu_C, int32_t n_cclips, int32_t cgroups, bool col_mean,
+                 const float* __restrict__ rscale, const float* __restrict__ cscale, float* __restrict__ out,
+                 int64_t ld_r, int64_t ld_c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x;
+  const int32_t r = static_cast<int32_t>(b / cgroups);
+  const int32_t c0 = (static_cast<int32_t>(b - static_cast<int64_t>(r) * cgroups) * 8 + (threadIdx.x >> 5)) * kRrCols;
+  if (c0 >= n_cclips) return;
+  const int32_t r0 = __ldg(cu_R + r), r1 = __ldg(cu_R + r + 1);
+  float v[kRrCols];
+  const float* src[kRrCols];
+#pragma unroll
+  for (int j = 0; j < kRrCols; ++j) {
+    v[j] = op_ident<kRowOp>();
+    src[j] = M + static_cast<int64_t>(min(c0 + j, n_cclips - 1)) * ldm;
+  }
+  for (int32_t i = r0 + lane; i < r1; i += 32) {
+#pragma unroll
+    for (int j = 0; j < kRrCols; ++j) v[j] = op_apply<kRowOp>(v[j], __ldcs(src[j] + i));
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+#pragma unroll
+    for (int j = 0; j < kRrCols; ++j) v[j] = op_apply<kRowOp>(v[j], __shfl_xor_sync(0xffffffffu, v[j], k));
+  }
+  float mine = v[0];
+#pragma unroll
+  for (int j = 1; j < kRrCols; ++j) mine = lane == j ? v[j] : mine;
+  const int32_t c = c0 + lane;
+  if (lane < kRrCols && c < n_cclips) {
+    float sc = (rscale ? __ldg(rscale + r) : 1.0f) * (cscale ? __ldg(cscale + c) : 1.0f);
+    if constexpr (kRowOp == OP_SUM) sc *= 1.0f / static_cast<float>(r1 - r0);
+    if (col_mean) sc *= 1.0f / static_cast<float>(__ldg(cu_C + c + 1) - __ldg(cu_C + c));
+    out[static_cast<int64_t>(r) * ld_r + static_cast<int64_t>(c) * ld_c] = mine * sc;
+  }
+}
+
 }  // namespace
+
+int launch_rowreduce(jegal_ctx* ctx, const float* M, int64_t ldm, const int32_t* cu_R, int32_t n_rclips,
+                     const int32_t* cu_C, int32_t n_cclips, int row_op, bool col_mean, const float* rscale,
+                     const float* cscale, float* out, int64_t ld_r, int64_t ld_c, cudaStream_t stream) {
+  const int32_t cgroups = (n_cclips + 8 * kRrCols - 1) / (8 * kRrCols);
+  const int64_t blocks = static_cast<int64_t>(n_rclips) * cgroups;
+  if (blocks <= 0) return JEGAL_OK;
+  if (blocks > 0x7fffffff) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "rowreduce: more than 2^31 blocks");
+  if (row_op == OP_MAX) {
+    rowreduce_kernel<OP_MAX><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        M, ldm, cu_R, n_rclips, cu_C, n_cclips, cgroups, col_mean, rscale, cscale, out, ld_r, ld_c);
+  } else {
+    rowreduce_kernel<OP_SUM><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        M, ldm, cu_R, n_rclips, cu_C, n_cclips, cgroups, col_mean, rscale, cscale, out, ld_r, ld_c);
+  }
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
+}
 
 int launch_simpool(jegal_ctx* ctx, int cta_group, int col_op, int row_op, const CUtensorMap& tmR,
                    const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream) {
