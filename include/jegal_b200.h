@@ -110,9 +110,12 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout,
 
 /* Host-only planning step of K1 (no device, no ctx): how the clips of the column-side operand are
  * packed into tiles of `width` (128 or 256) columns.  Whole clips are packed greedily; a clip
- * longer than `width` is cut into `partial` tiles when allow_split (legal only when both pooling
- * reductions are the same operation), otherwise JEGAL_ERR_UNSUPPORTED is returned with *n_out =
- * the offending clip.  Bit j of endmask[c] marks column 32c+j as the last column of a clip.
+ * longer than `width` is cut into pieces, one tile each, when allow_split (the fused single-pass
+ * kernel can combine pieces only when both pooling reductions are the same operation; the two-pass
+ * mode always can), otherwise JEGAL_ERR_UNSUPPORTED is returned with *n_out = the offending clip.
+ * partial: bit 0 = the tile is a piece of a split clip; bits 1.. = pieces beyond the first of all
+ * split clips before this tile, i.e. the tile's first column segment is number clip0 + (partial >> 1).
+ * Bit j of endmask[c] marks column 32c+j as the last column of a segment.
  * out may be NULL to query the count; at most max_out tiles are written. */
 typedef struct {
   int32_t row0, n_valid, clip0, partial;

@@ -45,6 +45,7 @@ int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_
   out->clear();
   *any_partial = false;
   int32_t i = 0;
+  int32_t extra = 0;  // pieces of split clips beyond the first, so far
   while (i < n_clips) {
     const int32_t len = cu[i + 1] - cu[i];
     if (len > width) {
@@ -57,11 +58,12 @@ int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_
         t.row0 = cu[i] + off;
         t.n_valid = std::min(width, len - off);
         t.clip0 = i;
-        t.partial = 1;
+        t.partial = 1 | (extra << 1);
         const int32_t e = t.n_valid - 1;
         t.endmask[e >> 5] |= 1u << (e & 31);
         out->push_back(t);
         *any_partial = true;
+        if (off + width < len) ++extra;
       }
       ++i;
       continue;
@@ -69,6 +71,7 @@ int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_
     CTile t{};
     t.row0 = cu[i];
     t.clip0 = i;
+    t.partial = extra << 1;
     int32_t used = 0;
     while (i < n_clips) {
       const int32_t l = cu[i + 1] - cu[i];
@@ -97,6 +100,14 @@ int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_sp
                                 std::to_string(L->cu_host[bad + 1] - L->cu_host[bad]) +
                                 " rows on the column side; a max-then-mean pooling needs <= " + std::to_string(width));
   set->n = static_cast<int>(set->host.size());
+  set->extra_pieces = 0;
+  if (set->any_partial) {
+    const int32_t w = width;
+    for (int32_t c = 0; c < L->n_clips; ++c) {
+      const int32_t len = L->cu_host[c + 1] - L->cu_host[c];
+      if (len > w) set->extra_pieces += (len + w - 1) / w - 1;
+    }
+  }
   return JEGAL_OK;
 }
 
@@ -122,8 +133,23 @@ int get_ctiles(jegal_ctx* ctx, jegal_layout* L, int width, bool allow_split, cud
       e = cudaMemcpyAsync(set->dev, set->host.data(), sizeof(CTile) * set->n, cudaMemcpyHostToDevice, stream);
     // one-time cost: later calls may run on another stream
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess && set->any_partial) {  // first segment number of every clip, for the two-pass mode
+      std::vector<int32_t> seg(L->n_clips + 1);
+      int32_t extra = 0;
+      for (int32_t c = 0; c < L->n_clips; ++c) {
+        seg[c] = c + extra;
+        const int32_t len = L->cu_host[c + 1] - L->cu_host[c];
+        if (len > width) extra += (len + width - 1) / width - 1;
+      }
+      seg[L->n_clips] = L->n_clips + extra;
+      e = cudaMalloc(&set->seg_dev, sizeof(int32_t) * seg.size());
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(set->seg_dev, seg.data(), sizeof(int32_t) * seg.size(), cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
     if (e != cudaSuccess) {
       if (set->dev) cudaFree(set->dev);
+      if (set->seg_dev) cudaFree(set->seg_dev);
       delete set;
       return set_err(ctx, JEGAL_ERR_CUDA, std::string("ctile upload: ") + cudaGetErrorString(e));
     }
@@ -254,6 +280,7 @@ void jegal_layout_destroy(jegal_layout* L) {
   if (L->rowinfo_dev) cudaFree(L->rowinfo_dev);
   for (auto* s : L->ctile_sets) {
     if (s->dev) cudaFree(s->dev);
+    if (s->seg_dev) cudaFree(s->seg_dev);
     delete s;
   }
   delete L;
@@ -321,6 +348,15 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
 
   jegal_layout::CTileSet* cts = nullptr;
   int rc = get_ctiles(ctx, LC, width, col_op == row_op, stream, &cts);
+  // A max-then-mean pooling cannot combine the pieces of a column clip longer than the tile after the
+  // row reduction; the two-pass mode can (its second pass sees the per-row values of every piece).
+  bool need_two_pass = false;
+  std::string unsupported_why;
+  if (rc == JEGAL_ERR_UNSUPPORTED && col_op != row_op) {
+    unsupported_why = ctx->err;
+    rc = get_ctiles(ctx, LC, width, true, stream, &cts);
+    need_two_pass = true;
+  }
   if (rc != JEGAL_OK) return rc;
 
   SimpoolParams p{};
@@ -355,15 +391,15 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   // extra HBM traffic, no atomics, no output initialisation, bitwise reproducible.
   // JEGAL_ROWMAT: -1 auto (default), 0 never, 1 always; JEGAL_ROWMAT_MAX_MB bounds the workspace (default 1024).
   const int64_t ldm = (LR->rows + 31) & ~static_cast<int64_t>(31);
-  const int64_t ws_elems = ldm * LC->n_clips;
+  const int64_t ws_elems = ldm * (static_cast<int64_t>(LC->n_clips) + cts->extra_pieces);  // one row per column segment
   bool two_pass = false;
   {
     const int mode = env_int("JEGAL_ROWMAT", -1);
     const int64_t max_bytes = static_cast<int64_t>(env_int("JEGAL_ROWMAT_MAX_MB", 1024)) << 20;
-    const bool fits = ws_elems * 4 <= max_bytes && ldm < (1ll << 31) && !cts->any_partial && !p.dense;
+    const bool fits = ws_elems * 4 <= max_bytes && ldm < (1ll << 31) && !p.dense;
     // auto: column clips shorter than 48 rows on average (>= ~5.3 segments per 256-column tile)
     const bool many_short = LC->rows < static_cast<int64_t>(48) * LC->n_clips;
-    two_pass = fits && (mode == 1 || (mode < 0 && many_short));
+    two_pass = fits && (mode == 1 || (mode != 0 && need_two_pass) || (mode < 0 && many_short));
   }
   if (two_pass) {
     if (ctx->rowmat_ws_elems < static_cast<size_t>(ws_elems)) {
@@ -382,6 +418,10 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
       }
     }
   }
+  if (need_two_pass && !two_pass)
+    return set_err(ctx, JEGAL_ERR_UNSUPPORTED,
+                   unsupported_why + " in one pass; the two-pass mode needs a workspace of " +
+                       std::to_string((ws_elems * 4) >> 20) + " MB (JEGAL_ROWMAT_MAX_MB, JEGAL_ROWMAT)");
   const int final_row_op = row_op;
   if (two_pass) {
     p.out = ctx->rowmat_ws;
@@ -400,8 +440,8 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   }
   auto finish = [&]() -> int {
     if (!two_pass) return JEGAL_OK;
-    return launch_rowreduce(ctx, ctx->rowmat_ws, ldm, LR->cu_dev, LR->n_clips, LC->cu_dev, LC->n_clips, final_row_op,
-                            col_op == OP_SUM, cols_are_gest ? cscale_dev : gscale_dev,
+    return launch_rowreduce(ctx, ctx->rowmat_ws, ldm, LR->cu_dev, LR->n_clips, LC->cu_dev, cts->seg_dev, LC->n_clips,
+                            col_op, final_row_op, cols_are_gest ? cscale_dev : gscale_dev,
                             cols_are_gest ? gscale_dev : cscale_dev, scores_dev, cols_are_gest ? ld_c : ld_g,
                             cols_are_gest ? ld_g : ld_c, stream);
   };

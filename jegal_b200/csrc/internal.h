@@ -22,7 +22,8 @@ struct CTile {
   int32_t row0;     // first operand row of the tile
   int32_t n_valid;  // columns that belong to this tile's clips
   int32_t clip0;    // first clip index
-  int32_t partial;  // 1: the tile holds a piece of a split clip -> results are combined atomically
+  int32_t partial;  // bit 0: the tile holds a piece of a split clip (fused mode: combined atomically);
+                    // bits 1..: extra pieces before this tile -> its first segment is number clip0 + (partial >> 1)
   uint32_t endmask[8];  // bit j of word c: column 32c+j is the last column of a segment
 };
 static_assert(sizeof(CTile) == 48, "CTile layout");
@@ -84,6 +85,8 @@ struct jegal_layout {
     int width = 0;
     bool allow_split = false;
     bool any_partial = false;
+    int32_t extra_pieces = 0;      // segments - clips (pieces of split clips beyond the first)
+    int32_t* seg_dev = nullptr;    // any_partial only: [n_clips + 1] first segment number of every clip
     int n = 0;
     std::vector<jegal::CTile> host;
     jegal::CTile* dev = nullptr;
@@ -106,9 +109,11 @@ int set_err(jegal_ctx* ctx, int code, const std::string& msg);
 int launch_simpool(jegal_ctx* ctx, int cta_group, int col_op, int row_op, const CUtensorMap& tmR,
                    const CUtensorMap& tmC, const SimpoolParams& p, cudaStream_t stream);
 // pass 2 of the two-pass mode: out[r * ld_r + c * ld_c] = rscale[r] * cscale[c] * ROWOP_{row in clip r} M[c * ldm + row]
-// (mean: the sum is divided by the clip's rows; col_mean: also by the column clip's rows)
+// (row mean: the sum is divided by the clip's rows; col_op == OP_SUM: also by the column clip's rows)
+// seg_C (nullable): column clip c owns the rows [seg_C[c], seg_C[c+1]) of M (pieces of a split clip, combined
+// with col_op); null: row c.
 int launch_rowreduce(jegal_ctx* ctx, const float* M, int64_t ldm, const int32_t* cu_R, int32_t n_rclips,
-                     const int32_t* cu_C, int32_t n_cclips, int row_op, bool col_mean, const float* rscale,
+                     const int32_t* cu_C, const int32_t* seg_C, int32_t n_cclips, int col_op, int row_op, const float* rscale,
                      const float* cscale, float* out, int64_t ld_r, int64_t ld_c, cudaStream_t stream);
 int launch_fill_f32(jegal_ctx* ctx, float* dst, int64_t n, float value, cudaStream_t stream);
 int launch_rowinfo(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,

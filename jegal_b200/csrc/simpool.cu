@@ -463,7 +463,9 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       const CTile* ctile = p.ctiles + ct;
       const int32_t n_valid = __ldg(&ctile->n_valid);
       const int32_t clip0 = __ldg(&ctile->clip0);
-      const bool col_partial = __ldg(&ctile->partial) != 0;
+      const int32_t part = __ldg(&ctile->partial);
+      const bool col_partial = (part & 1) != 0;
+      const int32_t seg0 = clip0 + (part >> 1);  // two-pass mode: M row of the tile's first segment
       const uint32_t my_em = lane < 8 ? __ldg(&ctile->endmask[lane]) : 0u;
       const int nchunks = (n_valid + 31) >> 5;
       int4 ri_next = make_int4(-1, 0, 1, 0);
@@ -539,7 +541,7 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
 
         float acc = op_ident<kColOp>();
         int32_t cclip = clip0;
-        float* m_ptr = rc.out_row + static_cast<int64_t>(clip0) * p.ld_c;  // two-pass mode: &M[clip0][row]
+        float* m_ptr = rc.out_row + static_cast<int64_t>(seg0) * p.ld_c;  // two-pass mode: &M[seg0][row]
         uint32_t va[32], vb[32];  // two chunks in flight: load c+1 while chunk c is pooled
         tmem_ld_32x32(t_addr, va);
         for (int ch = 0; ch < nchunks; ch += 2) {
@@ -655,12 +657,12 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float value)
 // butterfly finishes each reduction, lanes 0..kRrCols-1 write the scores.  The 8 warps of a block take
 // 8 * kRrCols consecutive column clips of one row clip.
 constexpr int kRrCols = 4;
-template <int kRowOp>
+template <int kColOp, int kRowOp>
 __global__ void __launch_bounds__(256)
 rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __restrict__ cu_R, int32_t n_rclips,
-                 const int32_t* __restrict__ cu_C, int32_t n_cclips, int32_t cgroups, bool col_mean,
-                 const float* __restrict__ rscale, const float* __restrict__ cscale, float* __restrict__ out,
-                 int64_t ld_r, int64_t ld_c) {
+                 const int32_t* __restrict__ cu_C, const int32_t* __restrict__ seg_C, int32_t n_cclips,
+                 int32_t cgroups, const float* __restrict__ rscale, const float* __restrict__ cscale,
+                 float* __restrict__ out, int64_t ld_r, int64_t ld_c) {
   const int lane = threadIdx.x & 31;
   const int64_t b = blockIdx.x;
   const int32_t r = static_cast<int32_t>(b / cgroups);
@@ -668,15 +670,29 @@ rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __rest
   if (c0 >= n_cclips) return;
   const int32_t r0 = __ldg(cu_R + r), r1 = __ldg(cu_R + r + 1);
   float v[kRrCols];
-  const float* src[kRrCols];
+  if (seg_C == nullptr) {  // one M row per column clip
+    const float* src[kRrCols];
 #pragma unroll
-  for (int j = 0; j < kRrCols; ++j) {
-    v[j] = op_ident<kRowOp>();
-    src[j] = M + static_cast<int64_t>(min(c0 + j, n_cclips - 1)) * ldm;
-  }
-  for (int32_t i = r0 + lane; i < r1; i += 32) {
+    for (int j = 0; j < kRrCols; ++j) {
+      v[j] = op_ident<kRowOp>();
+      src[j] = M + static_cast<int64_t>(min(c0 + j, n_cclips - 1)) * ldm;
+    }
+    for (int32_t i = r0 + lane; i < r1; i += 32) {
 #pragma unroll
-    for (int j = 0; j < kRrCols; ++j) v[j] = op_apply<kRowOp>(v[j], __ldcs(src[j] + i));
+      for (int j = 0; j < kRrCols; ++j) v[j] = op_apply<kRowOp>(v[j], __ldcs(src[j] + i));
+    }
+  } else {  // split column clips: combine the pieces of a clip per row (col_op) before reducing over rows
+#pragma unroll
+    for (int j = 0; j < kRrCols; ++j) {
+      v[j] = op_ident<kRowOp>();
+      const int32_t c = min(c0 + j, n_cclips - 1);
+      const int32_t m0 = __ldg(seg_C + c), m1 = __ldg(seg_C + c + 1);
+      for (int32_t i = r0 + lane; i < r1; i += 32) {
+        float x = op_ident<kColOp>();
+        for (int32_t m = m0; m < m1; ++m) x = op_apply<kColOp>(x, __ldcs(M + static_cast<int64_t>(m) * ldm + i));
+        v[j] = op_apply<kRowOp>(v[j], x);
+      }
+    }
   }
 #pragma unroll
   for (int k = 16; k > 0; k >>= 1) {
@@ -690,7 +706,7 @@ rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __rest
   if (lane < kRrCols && c < n_cclips) {
     float sc = (rscale ? __ldg(rscale + r) : 1.0f) * (cscale ? __ldg(cscale + c) : 1.0f);
     if constexpr (kRowOp == OP_SUM) sc *= 1.0f / static_cast<float>(r1 - r0);
-    if (col_mean) sc *= 1.0f / static_cast<float>(__ldg(cu_C + c + 1) - __ldg(cu_C + c));
+    if constexpr (kColOp == OP_SUM) sc *= 1.0f / static_cast<float>(__ldg(cu_C + c + 1) - __ldg(cu_C + c));
     out[static_cast<int64_t>(r) * ld_r + static_cast<int64_t>(c) * ld_c] = mine * sc;
   }
 }
@@ -698,18 +714,25 @@ rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __rest
 }  // namespace
 
 int launch_rowreduce(jegal_ctx* ctx, const float* M, int64_t ldm, const int32_t* cu_R, int32_t n_rclips,
-                     const int32_t* cu_C, int32_t n_cclips, int row_op, bool col_mean, const float* rscale,
-                     const float* cscale, float* out, int64_t ld_r, int64_t ld_c, cudaStream_t stream) {
+                     const int32_t* cu_C, const int32_t* seg_C, int32_t n_cclips, int col_op, int row_op,
+                     const float* rscale, const float* cscale, float* out, int64_t ld_r, int64_t ld_c,
+                     cudaStream_t stream) {
   const int32_t cgroups = (n_cclips + 8 * kRrCols - 1) / (8 * kRrCols);
   const int64_t blocks = static_cast<int64_t>(n_rclips) * cgroups;
   if (blocks <= 0) return JEGAL_OK;
   if (blocks > 0x7fffffff) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "rowreduce: more than 2^31 blocks");
-  if (row_op == OP_MAX) {
-    rowreduce_kernel<OP_MAX><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-        M, ldm, cu_R, n_rclips, cu_C, n_cclips, cgroups, col_mean, rscale, cscale, out, ld_r, ld_c);
+  const unsigned g = static_cast<unsigned>(blocks);
+  if (col_op == OP_MAX && row_op == OP_SUM) {
+    rowreduce_kernel<OP_MAX, OP_SUM><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, cgroups,
+                                                            rscale, cscale, out, ld_r, ld_c);
+  } else if (col_op == OP_MAX && row_op == OP_MAX) {
+    rowreduce_kernel<OP_MAX, OP_MAX><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, cgroups,
+                                                            rscale, cscale, out, ld_r, ld_c);
+  } else if (col_op == OP_SUM && row_op == OP_SUM) {
+    rowreduce_kernel<OP_SUM, OP_SUM><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, cgroups,
+                                                            rscale, cscale, out, ld_r, ld_c);
   } else {
-    rowreduce_kernel<OP_SUM><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-        M, ldm, cu_R, n_rclips, cu_C, n_cclips, cgroups, col_mean, rscale, cscale, out, ld_r, ld_c);
+    return set_err(ctx, JEGAL_ERR_ARG, "rowreduce: unsupported (col_op,row_op)");
   }
   JEGAL_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;

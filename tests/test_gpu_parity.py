@@ -95,10 +95,22 @@ def test_simpool_long_clips_split_across_tiles(dev, mode):
     assert np.abs(scoring.score_allpairs(gest, cont, mode) - ref).max() < TOL
 
 
-def test_simpool_rejects_overlong_clip_for_max_then_mean(dev):
+@pytest.mark.parametrize("mode", oracle.POOL_MODES)
+def test_simpool_overlong_clips_any_mode_two_pass(dev, mode):
+    """Clips longer than the 256-column tile on the first-reduced side: a max-then-mean pooling cannot
+    combine the pieces after the row reduction, so the library switches to the two-pass mode."""
+    from jegal_b200 import scoring
+    gest = rand_clips(3, 300, 700, 16) + rand_clips(4, 20, 90, 26)
+    cont = rand_clips(2, 257, 420, 17) + rand_clips(5, 3, 30, 27)
+    ref = oracle.simpool_allpairs(gest, cont, mode)
+    assert np.abs(scoring.score_allpairs(gest, cont, mode) - ref).max() < TOL
+
+
+def test_simpool_rejects_overlong_clip_without_workspace(dev, monkeypatch):
     from jegal_b200 import scoring
     from jegal_b200._lib import JegalError
     gest, cont = rand_clips(2, 300, 300, 16), rand_clips(2, 8, 8, 17)
+    monkeypatch.setenv("JEGAL_ROWMAT_MAX_MB", "0")
     with pytest.raises(JegalError, match="max-then-mean"):
         scoring.score_allpairs(gest, cont, "max_t_mean_w")
 
@@ -117,6 +129,37 @@ def test_simpool_fp16_operands_and_kernel_arithmetic(dev):
             same = oracle.simpool_allpairs(gest, cont, mode, rows_g=g16.float().cpu(), rows_c=c16.float().cpu())
             assert np.abs(got - same).max() < 1e-5, (dt, mode)
             assert np.abs(got - oracle.simpool_allpairs(gest, cont, mode)).max() < (TOL if dt == torch.bfloat16 else 3e-4)
+
+
+@pytest.mark.parametrize("case", ["ragged_avs", "tile_straddle", "tiny", "len1"])
+@pytest.mark.parametrize("mode", oracle.POOL_MODES)
+def test_simpool_two_pass_mode_matches_fused_and_oracle(dev, monkeypatch, case, mode):
+    """JEGAL_ROWMAT=1 forces the two-pass K1 (per-row values -> row-reduce kernel), 0 the fused epilogue.
+    Both must meet the oracle; the two-pass result has no atomics, so it is bitwise reproducible."""
+    from jegal_b200 import scoring
+    gest, cont = CASES[case][0](), CASES[case][1]()
+    ref = oracle.simpool_allpairs(gest, cont, mode)
+    monkeypatch.setenv("JEGAL_ROWMAT", "1")
+    two_a = scoring.score_allpairs(gest, cont, mode)
+    two_b = scoring.score_allpairs(gest, cont, mode)
+    two_t = scoring.score_allpairs(gest, cont, mode, content_major=True)
+    monkeypatch.setenv("JEGAL_ROWMAT", "0")
+    fused = scoring.score_allpairs(gest, cont, mode)
+    assert np.abs(two_a - ref).max() < TOL and np.abs(fused - ref).max() < TOL
+    assert np.array_equal(two_a, two_b) and np.array_equal(two_a, two_t.T)
+    assert np.abs(two_a - fused).max() < 1e-5
+
+
+def test_simpool_two_pass_cta_group_1_and_workspace_limit(dev, monkeypatch):
+    from jegal_b200 import scoring
+    gest, cont = rand_clips(25, 25, 120, 22), rand_clips(31, 4, 40, 23)
+    ref = oracle.simpool_allpairs(gest, cont, "max_w_mean_t")
+    monkeypatch.setenv("JEGAL_ROWMAT", "1")
+    monkeypatch.setenv("JEGAL_CTA_GROUP", "1")
+    assert np.abs(scoring.score_allpairs(gest, cont, "max_w_mean_t") - ref).max() < TOL
+    monkeypatch.setenv("JEGAL_CTA_GROUP", "2")
+    monkeypatch.setenv("JEGAL_ROWMAT_MAX_MB", "0")  # workspace does not fit -> fused single pass, same answer
+    assert np.abs(scoring.score_allpairs(gest, cont, "max_w_mean_t") - ref).max() < TOL
 
 
 def test_cta_group_1_and_2_agree(dev, monkeypatch):

@@ -137,13 +137,17 @@ def _check_plan(lengths, width, allow_split):
     cu = np.concatenate([[0], np.cumsum(lengths)])
     covered = np.zeros(cu[-1], dtype=np.int32)
     next_clip = 0
+    next_seg = 0
     for t in tiles:
-        row0, n_valid, clip0, partial = (int(x) for x in t[:4])
+        row0, n_valid, clip0, part = (int(x) for x in t[:4])
+        partial, seg0 = part & 1, clip0 + (part >> 1)
+        assert seg0 == next_seg  # segments (whole clips and pieces of split clips) are numbered in tile order
         mask = t[4:]
         assert 1 <= n_valid <= width
         covered[row0:row0 + n_valid] += 1
         ends = [c * 32 + j for c in range(8) for j in range(32) if (int(mask[c]) >> j) & 1]
         assert ends and ends[-1] == n_valid - 1
+        next_seg += len(ends)
         if partial:
             assert allow_split and len(ends) == 1 and lengths[clip0] > width
             assert cu[clip0] <= row0 and row0 + n_valid <= cu[clip0 + 1]
