@@ -203,6 +203,19 @@ int jegal_topk_exchange(jegal_ctx* ctx, jegal_exchange* ex, const float* scores_
 int jegal_group_softmax(jegal_ctx* ctx, const float* scores_dev, int32_t n_groups, int32_t group_size,
                         int64_t stride, float tau, float* probs_dev, int32_t* argmax_dev, void* stream);
 
+/* K5 — word-level mean pooling of the content branch (the producer side of the scoring path):
+ * out[s, col_off : col_off + dim] = mean of the feature rows x[seg_begin[s] : seg_end[s]] (end exclusive).
+ * Replaces the per-word Python loops of JEGAL.get_word_level_embs (models/jegal.py:141-198: sub-word
+ * tokens of a word :173-179, audio frames of a word :188-196) and get_audio_word_level_embs (:218-245);
+ * ranges may overlap (the reference's frame ranges are end-inclusive) or leave gaps.  A one-row range
+ * copies the row.  x is [rows, dim] dense in `in_dtype`; out has row stride ld_out (elements) in
+ * `out_dtype`, so the audio and text halves can be written into the concatenated fusion input
+ * (models/jegal.py:405-406) directly.  dim, ld_out and col_off must be multiples of 8; seg_* are
+ * device int32 arrays the caller validated (0 <= begin < end <= rows). */
+int jegal_segment_mean(jegal_ctx* ctx, const void* x_dev, int in_dtype, int64_t rows, int32_t dim,
+                       const int32_t* seg_begin_dev, const int32_t* seg_end_dev, int32_t n_seg, void* out_dev,
+                       int out_dtype, int64_t ld_out, int32_t col_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,7 @@ SYMBOLS = [
     "jegal_exchange_connect",
     "jegal_exchange_destroy",
     "jegal_topk_exchange",
+    "jegal_segment_mean",
 ]
 
 F32, F16, BF16 = 0, 1, 2
@@ -115,6 +116,8 @@ def load() -> C.CDLL:
         lib.jegal_exchange_destroy.argtypes = [vp]
         lib.jegal_exchange_destroy.restype = None
         lib.jegal_topk_exchange.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
+    if hasattr(lib, "jegal_segment_mean"):
+        lib.jegal_segment_mean.argtypes = [vp, vp, C.c_int, i64, i32, vp, vp, i32, vp, C.c_int, i64, i32, vp]
     if hasattr(lib, "jegal_plan_column_tiles"):
         lib.jegal_plan_column_tiles.argtypes = [C.POINTER(i32), i32, i32, i32, vp, i32, C.POINTER(i32)]
     for name in SYMBOLS:

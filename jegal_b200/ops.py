@@ -331,6 +331,34 @@ def group_softmax(scores: torch.Tensor, n_groups: int, group_size: int, stride: 
     return probs, argmax
 
 
+def segment_mean(x: torch.Tensor, seg_begin: torch.Tensor, seg_end: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 col_off: int = 0, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """K5: out[s, col_off:col_off+D] = mean(x[seg_begin[s]:seg_end[s]], dim=0) for every segment, one launch.
+
+    ``x`` is a dense CUDA [rows, D] matrix (fp32/fp16/bf16, D a multiple of 8); ``seg_begin`` / ``seg_end`` are
+    int32 CUDA vectors (end exclusive, ranges may overlap).  ``out`` may be a wider [n_seg, ld] matrix that
+    receives the result at column ``col_off`` (the concat fusion of models/jegal.py:405-406)."""
+    if not x.is_cuda or x.dim() != 2 or not x.is_contiguous() or x.dtype not in _DT:
+        raise JegalError("segment_mean: x must be a contiguous CUDA [rows, D] fp32/fp16/bf16 matrix")
+    for t in (seg_begin, seg_end):
+        if not t.is_cuda or t.dtype != torch.int32 or t.dim() != 1 or not t.is_contiguous():
+            raise JegalError("segment_mean: seg_begin / seg_end must be contiguous CUDA int32 vectors")
+    n = seg_begin.numel()
+    if seg_end.numel() != n:
+        raise JegalError("segment_mean: seg_begin and seg_end differ in length")
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty((n, col_off + dim), dtype=out_dtype or x.dtype, device=x.device)
+    if not out.is_cuda or out.dim() != 2 or out.shape[0] != n or out.stride(1) != 1 or out.dtype not in _DT:
+        raise JegalError("segment_mean: bad out tensor")
+    ctx = Context.get(x.device.index)
+    rc = ctx.lib.jegal_segment_mean(ctx.h, _ptr(x), _DT[x.dtype], rows, dim, _ptr(seg_begin), _ptr(seg_end), n,
+                                    _ptr(out), _DT[out.dtype], out.stride(0) if n > 0 else out.shape[1], col_off,
+                                    _stream())
+    ctx.check(rc, "jegal_segment_mean")
+    return out
+
+
 class TopkExchange:
     """C1: K2 + NVLink peer-memory exchange + merge for a gallery sharded over the ranks of one box.
 

@@ -9,6 +9,8 @@ What is pinned (reference file:line):
   retrieval.npz  get_similarity_matrix + compute_metrics   evaluation/evaluate_retrieval.py:38-65
   spotting.npz   get_attn_matrix + get_spotting_acc        evaluation/evaluate_spotting.py:39-90
   asd.npz        load_feats + get_similarity_cos + evaluate_asd   evaluation/evaluate_asd.py:26-127
+  wordlevel.npz  JEGAL.get_word_level_embs + get_audio_word_level_embs   models/jegal.py:131-252
+                 (method sources extracted with ast and executed: the module downloads XLM-R at import)
 """
 import contextlib
 import importlib.util
@@ -163,11 +165,93 @@ def golden_asd():
     print("asd: accuracies", acc)
 
 
+def ref_methods(names):
+    """models/jegal.py cannot be imported offline (AutoTokenizer.from_pretrained at :13-14), so the wanted
+    methods are cut out of its source with ast and compiled as plain functions (self is unused by them);
+    the module-level `tokenizer` they read is replaced by XLM-R's three special-token ids."""
+    import ast
+    import types
+
+    src = open(os.path.join(REF, "models", "jegal.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "tokenizer": types.SimpleNamespace(cls_token_id=0, sep_token_id=2, pad_token_id=1)}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, os.path.join(REF, "models", "jegal.py"), "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def wordlevel_inputs(seed=7, B=7, L=26, Tf=64, D=256):
+    """Tokenizer-shaped synthetic batch: <s> sub-words </s> <pad>..., offsets (0, n) for word starts."""
+    rng = np.random.default_rng(seed)
+    g = torch.Generator().manual_seed(seed)
+    text_emb = torch.randn(B, L, D, generator=g)
+    audio_emb = torch.randn(B, Tf, D, generator=g)
+    input_ids = np.ones((B, L), dtype=np.int64)  # pad = 1
+    offsets = np.zeros((B, L, 2), dtype=np.int64)
+    text, bounds = [], []
+    for b in range(B):
+        n_words = int(rng.integers(1, 8))
+        pos = 1
+        input_ids[b, 0] = 0
+        words = []
+        for w in range(n_words):
+            n_sub = int(rng.integers(1, 4))
+            if pos + n_sub >= L - 1:
+                break
+            c = 0
+            for k in range(n_sub):
+                ln = int(rng.integers(1, 5))
+                input_ids[b, pos] = int(rng.integers(5, 1000))
+                offsets[b, pos] = (c, c + ln)
+                c += ln
+                pos += 1
+            words.append(f"w{b}_{w}")
+        input_ids[b, pos] = 2
+        if b == 3:
+            words = words + ["extra1", "extra2"]  # more words than word starts -> invalid sample (:162-166)
+        text.append(words)
+        t0 = int(rng.integers(0, 200))
+        cuts = np.sort(rng.choice(np.arange(1, Tf - 1), size=len(words), replace=False)) if len(words) < Tf - 2 else None
+        wb, s0 = [], 0
+        for w, word in enumerate(words):
+            e0 = int(cuts[w])
+            wb.append([word, t0 + s0, t0 + e0])  # end-inclusive, next word starts on the same frame (overlap)
+            s0 = e0
+        bounds.append(wb)
+    return text_emb, audio_emb, torch.from_numpy(input_ids), torch.from_numpy(offsets), text, bounds
+
+
+def golden_wordlevel():
+    get_word, get_audio = ref_methods(["get_word_level_embs", "get_audio_word_level_embs"])
+    text_emb, audio_emb, input_ids, offsets, text, bounds = wordlevel_inputs()
+    wt, wa, inv = get_word(None, text_emb, text, input_ids, offsets, audio_emb=audio_emb, word_boundaries=bounds)
+    wt2, wa2, inv2 = get_word(None, text_emb, text, input_ids, offsets, audio_emb=None, word_boundaries=None)
+    assert wa2 == [] and inv2 == inv and all(torch.equal(a, b) for a, b in zip(wt, wt2))
+    au, inv_a = get_audio(None, audio_emb, bounds, list(inv))
+    # fp16 inputs (the .pkl dtype): the reference's mean keeps the dtype
+    wt_h, wa_h, _ = get_word(None, text_emb.half().float().half(), text, input_ids, offsets,
+                             audio_emb=audio_emb.half(), word_boundaries=bounds)
+    np.savez_compressed(
+        os.path.join(OUT, "wordlevel.npz"),
+        text_emb=text_emb.numpy(), audio_emb=audio_emb.numpy(), input_ids=input_ids.numpy(), offsets=offsets.numpy(),
+        n_words=np.int32([len(t) for t in text]),
+        bounds=np.int64([[wb[1], wb[2]] for b in bounds for wb in b]),
+        counts=np.int32([len(x) for x in wt]), invalid=np.int32(inv),
+        word_text=torch.cat(wt).numpy(), word_audio=torch.cat(wa).numpy(),
+        audio_only=torch.cat(au).numpy(), audio_only_counts=np.int32([len(x) for x in au]), audio_only_invalid=np.int32(inv_a),
+        word_text_f16=torch.cat(wt_h).numpy(), word_audio_f16=torch.cat(wa_h).numpy(),
+    )
+    print("wordlevel: words per valid clip", [len(x) for x in wt], "invalid", inv)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     golden_retrieval()
     golden_spotting()
     golden_asd()
+    golden_wordlevel()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

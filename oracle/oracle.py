@@ -22,6 +22,10 @@ Pinning status
     The mean/mean mode IS pinned: with the per-clip 1/||mean|| scales it must
     equal get_similarity_matrix on the mean-pooled clips (identity checked in
     tests/test_oracle_golden.py).
+  * word_level_* (models/jegal.py:131-252): PINNED — oracle/make_golden.py extracts the two
+    methods' source from models/jegal.py with `ast` (the module itself cannot be imported
+    offline: it downloads XLM-R at import, models/jegal.py:13-14) and executes them on synthetic
+    inputs; tests/golden/wordlevel.npz holds inputs and outputs.
 """
 from __future__ import annotations
 
@@ -214,3 +218,59 @@ def topk(scores, k: int) -> Tuple[np.ndarray, np.ndarray]:
     x = np.asarray(scores, dtype=np.float32)
     idx = np.argsort(-x, axis=1, kind="stable")[:, :k]
     return np.take_along_axis(x, idx, axis=1), idx.astype(np.int32)
+
+
+# ------------------------------------------------------------------ word-level pooling (producer side)
+def word_level_embs(text_emb, text, input_ids, offset_mapping, audio_emb=None, word_boundaries=None,
+                    special_token_ids=(0, 2, 1)):
+    """Restatement of JEGAL.get_word_level_embs (models/jegal.py:131-211), loop for loop."""
+    word_text, word_audio, invalid = [], [], []
+    for b in range(input_ids.shape[0]):
+        starts = [i for i, off in enumerate(offset_mapping[b])
+                  if int(off[0]) == 0 and int(input_ids[b][i]) not in special_token_ids]  # :146-149
+        et, ea, valid = [], [], True
+        if audio_emb is not None:
+            actual_start = int(word_boundaries[b][0][1])  # :155
+        for idx, _ in enumerate(text[b]):
+            if idx >= len(starts):  # :162-166
+                valid = False
+                invalid.append(b)
+                break
+            hi = starts[idx + 1] if idx < len(starts) - 1 else input_ids.shape[1]  # :168-171
+            sub = text_emb[b, starts[idx]:hi]
+            et.append(sub.mean(dim=0) if len(sub) > 1 else sub[0])  # :176-179
+            if audio_emb is not None:
+                s0 = int(word_boundaries[b][idx][1]) - actual_start
+                e0 = int(word_boundaries[b][idx][2]) - actual_start
+                fr = audio_emb[b, s0:e0 + 1]  # :188-191
+                ea.append(fr.mean(dim=0) if len(fr) > 1 else fr[0])  # :193-196
+        if valid:
+            if len(et) <= 0:
+                invalid.append(b)
+            else:
+                word_text.append(torch.stack(et))
+                if audio_emb is not None:
+                    word_audio.append(torch.stack(ea))
+    return word_text, word_audio, invalid
+
+
+def audio_word_level_embs(audio_emb, word_boundaries, invalid_sample_idx=None):
+    """Restatement of JEGAL.get_audio_word_level_embs (models/jegal.py:213-252)."""
+    out = []
+    for b in range(audio_emb.shape[0]):
+        if invalid_sample_idx is not None and b in invalid_sample_idx:
+            continue
+        actual_start = int(word_boundaries[b][0][1])
+        ea = []
+        for idx in range(len(word_boundaries[b])):
+            s0 = int(word_boundaries[b][idx][1]) - actual_start
+            e0 = int(word_boundaries[b][idx][2]) - actual_start
+            fr = audio_emb[b, s0:e0 + 1]
+            ea.append(fr.mean(dim=0) if len(fr) > 1 else fr[0])
+        if len(ea) > 0:
+            out.append(torch.stack(ea))
+        elif invalid_sample_idx is not None:
+            invalid_sample_idx.append(b)
+        else:
+            invalid_sample_idx = [b]
+    return out, invalid_sample_idx

@@ -47,7 +47,17 @@ def main():
     byts = rows * 1024 + gl.rows * 4 + cs.n * 9
     print(json.dumps({"stage": f"K3 spot (cfg3, {cs.n} clips)", "ms": ms, "clips_per_s": cs.n / ms * 1e3,
                       "GBps": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / hbm, "bytes": byts}))
-    del cs, g16, c16
+    # ---- K5 word-level pooling at the cfg3 shape: every word = mean of its frames' 256-d audio features (fp16)
+    feats = torch.randn(gl.rows, 256, device=dev).half()
+    sb = torch.from_numpy(np.concatenate([cs.cu_t[i] + np.asarray([b[1] for b in cs.boundaries[i]]) for i in range(cs.n)]).astype(np.int32)).to(dev)
+    se = torch.from_numpy(np.concatenate([cs.cu_t[i] + np.asarray([b[2] + 1 for b in cs.boundaries[i]]) for i in range(cs.n)]).astype(np.int32)).to(dev)
+    se = torch.minimum(se, torch.tensor(gl.rows, dtype=torch.int32, device=dev))
+    outw = torch.empty(sb.numel(), 256, dtype=torch.float16, device=dev)
+    ms = timeit(lambda: ops.segment_mean(feats, sb, se, out=outw))
+    byts = int((se - sb).sum().item()) * 512 + sb.numel() * 512 + sb.numel() * 8
+    print(json.dumps({"stage": f"K5 word-level mean pooling (cfg3 shape: {sb.numel()} words over {gl.rows} frames, D=256 fp16)",
+                      "ms": ms, "GBps": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / hbm, "bytes": byts}))
+    del cs, g16, c16, feats
     # ---- cfg4 ASD
     n4 = int(os.environ.get("CFG4_N", 10000))
     ds = synth.cfg4_asd(n4, 4, device=dev)

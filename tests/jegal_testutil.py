@@ -16,3 +16,16 @@ def gap_aware_equal(got_idx, ref_idx, ref_scores_of, tol=2e-3):
         if abs(ref_scores_of(n, ref_idx[n]) - ref_scores_of(n, got_idx[n])) > tol:
             bad.append(int(n))
     return bad
+
+
+def wordlevel_case(g):
+    """Rebuild the python-side inputs of tests/golden/wordlevel.npz (oracle/make_golden.py::wordlevel_inputs)."""
+    import torch
+
+    text, bounds, pos = [], [], 0
+    for b, n in enumerate(g["n_words"]):
+        text.append([f"w{b}_{w}" for w in range(int(n))])
+        bounds.append([[f"w{b}_{w}", int(g["bounds"][pos + w][0]), int(g["bounds"][pos + w][1])] for w in range(int(n))])
+        pos += int(n)
+    return (torch.from_numpy(g["text_emb"]), torch.from_numpy(g["audio_emb"]), torch.from_numpy(g["input_ids"]),
+            torch.from_numpy(g["offsets"]), text, bounds)

@@ -491,3 +491,64 @@ def test_empty_and_degenerate_inputs(dev):
     # a single one-frame / one-word pair
     one = scoring.score_allpairs([g[0][:1]], [g[1][:1]], "max_max")
     assert abs(one[0, 0] - float(oracle.cos_tile(g[0][:1], g[1][:1]))) < TOL
+
+
+# ----------------------------------------------------------------------------- K5 (word-level pooling)
+def test_wordlevel_golden_and_oracle(dev, golden):
+    """jegal_b200.wordlevel (one K5 launch per feature tensor) against the outputs of the reference's own
+    get_word_level_embs / get_audio_word_level_embs (tests/golden/wordlevel.npz)."""
+    from jegal_b200 import wordlevel
+    from jegal_testutil import wordlevel_case
+
+    g = golden("wordlevel")
+    text_emb, audio_emb, input_ids, offsets, text, bounds = wordlevel_case(g)
+    wt, wa, inv = wordlevel.get_word_level_embs(text_emb.to(dev), text, input_ids, offsets, audio_emb=audio_emb.to(dev),
+                                                word_boundaries=bounds)
+    assert inv == list(g["invalid"]) and [len(x) for x in wt] == list(g["counts"])
+    assert np.abs(torch.cat(wt).cpu().numpy() - g["word_text"]).max() < 1e-6      # fp32 sums, other order
+    assert np.abs(torch.cat(wa).cpu().numpy() - g["word_audio"]).max() < 1e-6
+    wt2, wa2, inv2 = wordlevel.get_word_level_embs(text_emb.to(dev), text, input_ids, offsets)
+    assert wa2 == [] and inv2 == inv and torch.equal(torch.cat(wt2), torch.cat(wt))
+    au, inv_a = wordlevel.get_audio_word_level_embs(audio_emb.to(dev), bounds, list(inv))
+    assert inv_a == list(g["audio_only_invalid"]) and [len(x) for x in au] == list(g["audio_only_counts"])
+    assert np.abs(torch.cat(au).cpu().numpy() - g["audio_only"]).max() < 1e-6
+    # fp16 in, fp16 out: fp32 accumulation and one rounding, like torch's mean -> at most 1 ulp apart
+    wt_h, wa_h, _ = wordlevel.get_word_level_embs(text_emb.half().to(dev), text, input_ids, offsets,
+                                                  audio_emb=audio_emb.half().to(dev), word_boundaries=bounds)
+    assert wt_h[0].dtype == torch.float16
+    assert np.abs(torch.cat(wt_h).float().cpu().numpy() - g["word_text_f16"].astype(np.float32)).max() < 2e-3
+    assert np.abs(torch.cat(wa_h).float().cpu().numpy() - g["word_audio_f16"].astype(np.float32)).max() < 2e-3
+    padded, lengths = wordlevel.pad_wordlevel_embs(wt)
+    assert lengths == list(g["counts"]) and padded.shape == (len(wt), max(lengths), 256)
+    assert float(padded[1, lengths[1]:].abs().sum()) == 0.0
+
+
+def test_segment_mean_random_ranges_dtypes_and_fused_concat(dev):
+    from jegal_b200 import ops
+    rng = np.random.default_rng(5)
+    rows, n = 5000, 700
+    b = rng.integers(0, rows - 1, n)
+    e = np.minimum(rows, b + rng.integers(1, 40, n))
+    sb, se = torch.from_numpy(b.astype(np.int32)).to(dev), torch.from_numpy(e.astype(np.int32)).to(dev)
+    for dt, tol in ((torch.float32, 1e-6), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)):
+        for dim in (256, 512, 264):
+            x = torch.randn(rows, dim, device=dev).to(dt)
+            want = torch.stack([x[int(lo):int(hi)].float().mean(0) for lo, hi in zip(b, e)])
+            got = ops.segment_mean(x, sb, se)
+            assert got.dtype == dt and (got.float() - want).abs().max() < tol, (dt, dim)
+    # audio half and text half written into one [n, 512] fusion input (models/jegal.py:405-406)
+    a, t = torch.randn(rows, 256, device=dev), torch.randn(rows, 256, device=dev)
+    fused = torch.empty(n, 512, device=dev)
+    ops.segment_mean(a, sb, se, out=fused, col_off=0)
+    ops.segment_mean(t, sb, se, out=fused, col_off=256)
+    want = torch.cat([ops.segment_mean(a, sb, se), ops.segment_mean(t, sb, se)], dim=-1)
+    assert torch.equal(fused, want)
+    one = ops.segment_mean(a, sb[:1], sb[:1] + 1)  # a one-row word is the row itself
+    assert torch.equal(one[0], a[int(b[0])])
+
+
+def test_wordlevel_empty_audio_range_raises_like_reference(dev):
+    from jegal_b200 import wordlevel
+    audio = torch.randn(1, 10, 256, device=dev)
+    with pytest.raises(IndexError):
+        wordlevel.get_audio_word_level_embs(audio, [[["a", 100, 104], ["b", 120, 125]]])  # second word starts past the clip

@@ -110,3 +110,22 @@ def test_topk_ties_prefer_lower_index():
     x = np.array([[1.0, 3.0, 3.0, 2.0, 3.0]], dtype=np.float32)
     v, i = oracle.topk(x, 4)
     assert i.tolist() == [[1, 2, 4, 3]] and v.tolist() == [[3.0, 3.0, 3.0, 2.0]]
+
+
+# ------------------------------------------------------------------ word-level pooling (models/jegal.py:131-252)
+def test_wordlevel_oracle_equals_reference_methods(golden):
+    import torch
+    from jegal_testutil import wordlevel_case
+
+    g = golden("wordlevel")
+    text_emb, audio_emb, input_ids, offsets, text, bounds = wordlevel_case(g)
+    wt, wa, inv = oracle.word_level_embs(text_emb, text, input_ids, offsets, audio_emb=audio_emb, word_boundaries=bounds)
+    assert inv == list(g["invalid"]) and [len(x) for x in wt] == list(g["counts"])
+    assert np.array_equal(torch.cat(wt).numpy(), g["word_text"]) and np.array_equal(torch.cat(wa).numpy(), g["word_audio"])
+    au, inv_a = oracle.audio_word_level_embs(audio_emb, bounds, list(inv))
+    assert inv_a == list(g["audio_only_invalid"]) and [len(x) for x in au] == list(g["audio_only_counts"])
+    assert np.array_equal(torch.cat(au).numpy(), g["audio_only"])
+    wt_h, wa_h, _ = oracle.word_level_embs(text_emb.half(), text, input_ids, offsets, audio_emb=audio_emb.half(),
+                                           word_boundaries=bounds)
+    assert np.array_equal(torch.cat(wt_h).numpy(), g["word_text_f16"])
+    assert np.array_equal(torch.cat(wa_h).numpy(), g["word_audio_f16"])
