@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Frame x word attention heatmap of one clip on the B200 kernels — drop-in for the scoring half
-of the reference's utils/plot_heatmap.py (same --path / --fname).  The matrix is computed by K3;
-rendering needs matplotlib + cv2 exactly as in the reference and is skipped (the matrix is saved
-as <fname>.npy) when they are not installed."""
+of the reference's utils/plot_heatmap.py (same --path / --fname).  The matrix is computed by K3 and
+saved as <fname>.npy; the picture is drawn by jegal_b200.render (jet colormap + the reference's
+thresholded overlay, standard library PNG writer: neither matplotlib nor cv2 is needed)."""
 import argparse
 import os
 import sys
@@ -27,18 +27,8 @@ def main():
     print("Attn mtx: ", attn_mtx.shape)
     print("Words: ", words)
     np.save(args.fname + ".npy", attn_mtx)
-    try:
-        import matplotlib
-        matplotlib.use("Agg")
-        import matplotlib.pyplot as plt
-        fig, ax = plt.subplots(1, 1, figsize=(16, 20))
-        im = ax.imshow(attn_mtx, cmap="jet")
-        ax.set_yticks(list(range(len(words))))
-        ax.set_yticklabels(words, fontsize=14)
-        fig.colorbar(im, ax=ax, fraction=0.02)
-        fig.savefig(args.fname + ".png")
-    except ImportError:
-        print("matplotlib not installed: wrote {}.npy only".format(args.fname))
+    from jegal_b200 import render
+    print("wrote", render.render_heatmap(attn_mtx, words, fname=args.fname))
     return attn_mtx, words
 
 

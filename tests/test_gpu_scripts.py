@@ -101,6 +101,7 @@ def test_plot_heatmap_script_and_index(pkl_dir, tmp_path):
     f = os.path.join(d, pkl_io.clip_pkl_name(names[0]))
     out = run("plot_heatmap.py", "--path", f, "--fname", str(tmp_path / "hm"))
     a = np.load(str(tmp_path / "hm.npy"))
+    assert open(str(tmp_path / "hm.png"), "rb").read(8) == b"\x89PNG\r\n\x1a\n"  # drawn without matplotlib
     ref = oracle.get_attn_matrix(cs.gesture(0).numpy(), cs.content(0).numpy(), normalize=False)
     assert a.shape == ref.shape and np.abs(a - ref).max() < 1.5e-2
     stats = index.build_from_pkl_dir(d, str(tmp_path / "idx"))

@@ -190,3 +190,26 @@ def test_ctx_create_fails_cleanly_without_gpu():
     assert rc == -2 and not h.value  # JEGAL_ERR_DEVICE, no context, no crash
     assert lib.jegal_last_error(None) == b"null ctx"
     assert lib.jegal_launch_count(None) == 0
+
+
+def test_heatmap_renderer_jet_blend_and_png(tmp_path):
+    """jegal_b200.render restates matplotlib's jet LUT and the overlay blend of utils/plot_heatmap.py:78-87."""
+    import struct
+    import zlib
+    from jegal_b200 import render
+    assert np.allclose(render.jet(np.array([0.0, 1.0])), [[0, 0, 0.5], [0.5, 0, 0]])
+    mid = render.jet(np.array([0.5]))[0]
+    assert abs(mid[1] - 1.0) < 1e-9 and abs(mid[0] - mid[2]) < 0.03  # green plateau, red ~ blue at the centre
+    attn = np.array([[0.05, 0.9, 0.3], [0.95, 0.0, 0.79]], dtype=np.float32)
+    rgb = render.heatmap_rgb(attn, thresh=0.8, alpha=0.6)
+    over, base = render.jet(np.array([0.01])), render.jet(np.array([0.05]))
+    want = 0.76 * (0.6 * over[0] + 0.4 * base[0]) + 0.24
+    assert np.allclose(rgb[0, 0], want)
+    path = render.render_heatmap(attn, ["hello", "world"], fname=str(tmp_path / "hm"), cell=4)
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h = struct.unpack(">II", raw[16:24])
+    assert (h, w) == (2 * 4, 3 * 4 + 4 + 4) and b"hello world" in raw
+    idat = raw[raw.index(b"IDAT") + 4: raw.index(b"IEND") - 8]
+    pix = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
+    assert np.array_equal(pix[0, 0], np.rint(want * 255).astype(np.uint8))
