@@ -180,11 +180,39 @@ __device__ __forceinline__ void store_chunk_dense(const uint32_t (&v)[32], int32
                                                   const RowCtx& rc, const SimpoolParams& p) {
   if (!(rc.flags & kRcValid)) return;
   float* dst = rc.out_row + static_cast<int64_t>(cclip) * p.ld_c;
+  const float rs = rc.rscale;
+  if (p.ld_c == 1 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(p.cscale + cclip)) & 15u) == 0u) {
+    // this thread's 32 cosines are contiguous in the output row: 16-byte stores (4x fewer store instructions)
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j + 3 < ncols) {
+        float4 o;
+        if (p.cscale) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.cscale + cclip + j));
+          o = make_float4(__uint_as_float(v[j]) * rs * sc.x, __uint_as_float(v[j + 1]) * rs * sc.y,
+                          __uint_as_float(v[j + 2]) * rs * sc.z, __uint_as_float(v[j + 3]) * rs * sc.w);
+        } else {
+          o = make_float4(__uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
+                          __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
+        }
+        __stcs(reinterpret_cast<float4*>(dst + j), o);
+      } else {
+#pragma unroll
+        for (int i = j; i < j + 4; ++i) {
+          if (i < ncols) {
+            const float sc = p.cscale ? __ldg(p.cscale + cclip + i) : 1.0f;
+            dst[i] = __uint_as_float(v[i]) * rs * sc;
+          }
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j < ncols) {
       const float sc = p.cscale ? __ldg(p.cscale + cclip + j) : 1.0f;
-      dst[static_cast<int64_t>(j) * p.ld_c] = __uint_as_float(v[j]) * rc.rscale * sc;
+      dst[static_cast<int64_t>(j) * p.ld_c] = __uint_as_float(v[j]) * rs * sc;
     }
   }
 }

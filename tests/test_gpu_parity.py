@@ -552,3 +552,28 @@ def test_wordlevel_empty_audio_range_raises_like_reference(dev):
     audio = torch.randn(1, 10, 256, device=dev)
     with pytest.raises(IndexError):
         wordlevel.get_audio_word_level_embs(audio, [[["a", 100, 104], ["b", 120, 125]]])  # second word starts past the clip
+
+
+def test_embedding_sink_device_path_equals_pkl_round_trip(dev, tmp_path):
+    """jegal_b200.producer: the model's outputs scored straight from the device (packed + K0) give the
+    same scores as the reference's route through normalised fp16 .pkl files (inference_embs.py:628-646)."""
+    from jegal_b200 import pkl_io, producer, scoring
+    g = torch.Generator(device="cpu").manual_seed(3)
+    sink = producer.EmbeddingSink(res_dir=str(tmp_path))
+    raw = []
+    for i, (T, W) in enumerate([(56, 8), (68, 7), (31, 5), (120, 12)]):
+        ge = (3.0 * torch.randn(1, T, 512, generator=g)).half().to(dev)   # un-normalised, as the model emits them
+        ce = (0.5 * torch.randn(1, W, 512, generator=g)).half().to(dev)
+        raw.append((ge, ce))
+        sink.add(ge, ce, {"fname": f"clip{i}", "word_boundaries": [["w", 0, T - 1]], "text": "w"})
+    gest, cont, infos = sink.finish()
+    assert gest.rows.dtype == torch.bfloat16 and gest.layout.n_clips == 4 and len(infos) == 4
+    d = pkl_io.load_dir(str(tmp_path))
+    assert len(d["files"]) == 4 and d["gesture"][0].dtype == np.float16
+    want0 = torch.nn.functional.normalize(raw[0][0], p=2, dim=-1)[0].cpu().numpy()
+    assert np.array_equal(d["gesture"][0], want0)  # the archival file follows the reference's recipe exactly
+    for mode in oracle.POOL_MODES:
+        from_dev = scoring.score_allpairs(gest, cont, mode, normalize_rows=False)
+        from_pkl = scoring.score_allpairs(d["gesture"], d["content"], mode)
+        ref = oracle.simpool_allpairs(d["gesture"], d["content"], mode)
+        assert np.abs(from_dev - ref).max() < TOL and np.abs(from_pkl - ref).max() < TOL
