@@ -40,12 +40,16 @@ int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, in
   return make_box_tmap_impl(ctx, out, rows_dev, n_rows, op_dtype, kTileRows);
 }
 
-int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_split,
-                      std::vector<CTile>* out, bool* any_partial, int32_t* bad_clip) {
+int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, int flags, std::vector<CTile>* out,
+                      bool* any_partial, int32_t* bad_clip, std::vector<int32_t>* seg_of_clip) {
+  const bool allow_split = (flags & kPlanAllowSplit) != 0;
+  const bool cut_halves = (flags & kPlanCutHalves) != 0;
+  const int32_t h = width / 2;
   out->clear();
   *any_partial = false;
+  if (seg_of_clip) seg_of_clip->assign(static_cast<size_t>(n_clips) + 1, 0);
   int32_t i = 0;
-  int32_t extra = 0;  // pieces of split clips beyond the first, so far
+  int32_t extra = 0;  // segments beyond one per clip, so far (pieces of split clips, half-tile cuts)
   while (i < n_clips) {
     const int32_t len = cu[i + 1] - cu[i];
     if (len > width) {
@@ -53,18 +57,25 @@ int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_
         *bad_clip = i;
         return JEGAL_ERR_UNSUPPORTED;
       }
+      if (seg_of_clip) (*seg_of_clip)[i] = i + extra;
+      int32_t segs_done = 0;
       for (int32_t off = 0; off < len; off += width) {
         CTile t{};
         t.row0 = cu[i] + off;
         t.n_valid = std::min(width, len - off);
         t.clip0 = i;
-        t.partial = 1 | (extra << 1);
+        t.partial = 1 | ((extra + segs_done) << 1);
         const int32_t e = t.n_valid - 1;
         t.endmask[e >> 5] |= 1u << (e & 31);
+        ++segs_done;
+        if (cut_halves && t.n_valid > h) {
+          t.endmask[(h - 1) >> 5] |= 1u << ((h - 1) & 31);
+          ++segs_done;
+        }
         out->push_back(t);
         *any_partial = true;
-        if (off + width < len) ++extra;
       }
+      extra += segs_done - 1;
       ++i;
       continue;
     }
@@ -72,6 +83,7 @@ int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_
     t.row0 = cu[i];
     t.clip0 = i;
     t.partial = extra << 1;
+    const int32_t first = i;
     int32_t used = 0;
     while (i < n_clips) {
       const int32_t l = cu[i + 1] - cu[i];
@@ -82,47 +94,52 @@ int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_
       ++i;
     }
     t.n_valid = used;
+    // two-pass mode with both warpgroups on every tile: no segment may cross the middle of the tile, so a
+    // clip that does is cut there (its two pieces are combined by the second pass like a split clip's)
+    const bool cut = cut_halves && used > h && !((t.endmask[(h - 1) >> 5] >> ((h - 1) & 31)) & 1u);
+    if (seg_of_clip)
+      for (int32_t c = first; c < i; ++c)
+        (*seg_of_clip)[c] = c + extra + ((cut && cu[c] - cu[first] >= h) ? 1 : 0);
+    if (cut) {
+      t.endmask[(h - 1) >> 5] |= 1u << ((h - 1) & 31);
+      ++extra;
+    }
     out->push_back(t);
   }
+  if (seg_of_clip) (*seg_of_clip)[n_clips] = n_clips + extra;
   return JEGAL_OK;
 }
 
 namespace {
 
-int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, bool allow_split,
-                 jegal_layout::CTileSet* set) {
+int build_ctiles(jegal_ctx* ctx, const jegal_layout* L, int width, int flags, jegal_layout::CTileSet* set) {
   set->width = width;
-  set->allow_split = allow_split;
+  set->flags = flags;
   int32_t bad = -1;
-  const int rc = plan_column_tiles(L->cu_host.data(), L->n_clips, width, allow_split, &set->host, &set->any_partial, &bad);
+  const int rc = plan_column_tiles(L->cu_host.data(), L->n_clips, width, flags, &set->host, &set->any_partial, &bad,
+                                   &set->seg_host);
   if (rc != JEGAL_OK)
     return set_err(ctx, rc, "clip " + std::to_string(bad) + " has " +
                                 std::to_string(L->cu_host[bad + 1] - L->cu_host[bad]) +
                                 " rows on the column side; a max-then-mean pooling needs <= " + std::to_string(width));
   set->n = static_cast<int>(set->host.size());
-  set->extra_pieces = 0;
-  if (set->any_partial) {
-    const int32_t w = width;
-    for (int32_t c = 0; c < L->n_clips; ++c) {
-      const int32_t len = L->cu_host[c + 1] - L->cu_host[c];
-      if (len > w) set->extra_pieces += (len + w - 1) / w - 1;
-    }
-  }
+  set->extra_pieces = set->seg_host[L->n_clips] - L->n_clips;
   return JEGAL_OK;
 }
 
-int get_ctiles(jegal_ctx* ctx, jegal_layout* L, int width, bool allow_split, cudaStream_t stream,
+int get_ctiles(jegal_ctx* ctx, jegal_layout* L, int width, int flags, cudaStream_t stream,
                jegal_layout::CTileSet** out) {
   for (auto* s : L->ctile_sets) {
     // a no-split set without partial tiles also serves callers that would allow splitting
-    if (s->width == width && (s->allow_split == allow_split || !s->any_partial)) {
+    if (s->width == width && (s->flags & kPlanCutHalves) == (flags & kPlanCutHalves) &&
+        ((s->flags & kPlanAllowSplit) == (flags & kPlanAllowSplit) || !s->any_partial)) {
       *out = s;
       return JEGAL_OK;
     }
   }
   auto* set = new (std::nothrow) jegal_layout::CTileSet();
   if (!set) return set_err(ctx, JEGAL_ERR_NOMEM, "out of host memory");
-  int rc = build_ctiles(ctx, L, width, allow_split, set);
+  int rc = build_ctiles(ctx, L, width, flags, set);
   if (rc != JEGAL_OK) {
     delete set;
     return rc;
@@ -131,22 +148,14 @@ int get_ctiles(jegal_ctx* ctx, jegal_layout* L, int width, bool allow_split, cud
     cudaError_t e = cudaMalloc(&set->dev, sizeof(CTile) * set->n);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(set->dev, set->host.data(), sizeof(CTile) * set->n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && set->extra_pieces > 0) {  // first segment number of every clip, for the two-pass mode
+      e = cudaMalloc(&set->seg_dev, sizeof(int32_t) * set->seg_host.size());
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(set->seg_dev, set->seg_host.data(), sizeof(int32_t) * set->seg_host.size(),
+                            cudaMemcpyHostToDevice, stream);
+    }
     // one-time cost: later calls may run on another stream
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e == cudaSuccess && set->any_partial) {  // first segment number of every clip, for the two-pass mode
-      std::vector<int32_t> seg(L->n_clips + 1);
-      int32_t extra = 0;
-      for (int32_t c = 0; c < L->n_clips; ++c) {
-        seg[c] = c + extra;
-        const int32_t len = L->cu_host[c + 1] - L->cu_host[c];
-        if (len > width) extra += (len + width - 1) / width - 1;
-      }
-      seg[L->n_clips] = L->n_clips + extra;
-      e = cudaMalloc(&set->seg_dev, sizeof(int32_t) * seg.size());
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(set->seg_dev, seg.data(), sizeof(int32_t) * seg.size(), cudaMemcpyHostToDevice, stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    }
     if (e != cudaSuccess) {
       if (set->dev) cudaFree(set->dev);
       if (set->seg_dev) cudaFree(set->seg_dev);
@@ -179,7 +188,7 @@ int jegal_plan_column_tiles(const int32_t* cu_len_host, int32_t n_clips, int32_t
   std::vector<CTile> tiles;
   bool any_partial = false;
   int32_t bad = -1;
-  const int rc = plan_column_tiles(cu_len_host, n_clips, width, allow_split != 0, &tiles, &any_partial, &bad);
+  const int rc = plan_column_tiles(cu_len_host, n_clips, width, allow_split & 3, &tiles, &any_partial, &bad, nullptr);
   if (rc != JEGAL_OK) {
     *n_out = bad;
     return rc;
@@ -346,63 +355,38 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   if (ctx->sm_count < 2) cg = 1;
   const int width = kTileRows * cg;
 
-  jegal_layout::CTileSet* cts = nullptr;
-  int rc = get_ctiles(ctx, LC, width, col_op == row_op, stream, &cts);
-  // A max-then-mean pooling cannot combine the pieces of a column clip longer than the tile after the
-  // row reduction; the two-pass mode can (its second pass sees the per-row values of every piece).
-  bool need_two_pass = false;
-  std::string unsupported_why;
-  if (rc == JEGAL_ERR_UNSUPPORTED && col_op != row_op) {
-    unsupported_why = ctx->err;
-    rc = get_ctiles(ctx, LC, width, true, stream, &cts);
-    need_two_pass = true;
-  }
-  if (rc != JEGAL_OK) return rc;
-
-  SimpoolParams p{};
-  p.ctiles = cts->dev;
-  p.n_ctiles = cts->n;
-  p.n_rtiles = static_cast<int32_t>((LR->rows + width - 1) / width);
-  // L2 plan: DRAM traffic of a launch = R once + (#phases) x C, because a column tile has no reuse
-  // inside a phase; so phases of R are made as large as stays L2-resident while every cluster
-  // re-streams them, and column tiles are fetched with evict_first so they do not displace R.
-  p.c_policy = env_int("JEGAL_C_POLICY", 2);
-  const int64_t chunk_bytes = static_cast<int64_t>(env_int("JEGAL_CHUNK_MB", 24)) << 20;
-  p.chunk_rtiles = static_cast<int32_t>(std::max<int64_t>(1, chunk_bytes / (static_cast<int64_t>(width) * kD * 2)));
-  p.n_rows_R = static_cast<int32_t>(LR->rows);
-  p.rowinfo_R = LR->rowinfo_dev;
-  p.uni_len_R = LR->uniform_len;
-  p.dense = (LR->uniform_len == 1 && LC->uniform_len == 1) ? 1 : 0;  // 1 x 1 tiles: all pooling modes coincide
-  p.cu_R = LR->cu_dev;
-  p.cu_C = LC->cu_dev;
-  p.rscale = cols_are_gest ? cscale_dev : gscale_dev;
-  p.cscale = cols_are_gest ? gscale_dev : cscale_dev;
-  p.out = scores_dev;
-  p.ld_r = cols_are_gest ? ld_c : ld_g;
-  p.ld_c = cols_are_gest ? ld_g : ld_c;
-  p.idesc = ptx::make_idesc_f16(op_dtype == JEGAL_BF16 ? 1u : 0u, static_cast<uint32_t>(width),
-                                static_cast<uint32_t>(width));
-
   // Two-pass mode.  The fused epilogue pays ~50 dependent instructions (segmented shuffles + an atomic) per
   // column clip per tile; with many short column clips (word clips on the column side: ~12 per tile) it
   // takes longer than the tile's MMAs (measured: 57 % of tensor peak on config 2, max_w_mean_t).  There K1
-  // only pools along columns and stores the per-row values as M[column clip][row] (one coalesced 128-byte
-  // store per warp and clip), and launch_rowreduce finishes over rows: 2 x rows x n_col_clips x 4 bytes of
-  // extra HBM traffic, no atomics, no output initialisation, bitwise reproducible.
+  // only pools along columns and stores the per-row values as M[column segment][row] (one coalesced 128-byte
+  // store per warp and segment), and launch_rowreduce finishes over rows: 2 x rows x segments x 4 bytes of
+  // extra HBM traffic, no atomics, no output initialisation, bitwise reproducible.  Its plan cuts segments
+  // at the middle of every tile, so each of the two epilogue warpgroups pools one half of EVERY tile.
   // JEGAL_ROWMAT: -1 auto (default), 0 never, 1 always; JEGAL_ROWMAT_MAX_MB bounds the workspace (default 1024).
+  const int rowmat_mode = env_int("JEGAL_ROWMAT", -1);
+  const bool dense = LR->uniform_len == 1 && LC->uniform_len == 1;  // 1 x 1 tiles: all pooling modes coincide
+  // auto: column clips shorter than 48 rows on average (>= ~5.3 segments per 256-column tile)
+  const bool many_short = LC->rows < static_cast<int64_t>(48) * LC->n_clips;
   const int64_t ldm = (LR->rows + 31) & ~static_cast<int64_t>(31);
-  const int64_t ws_elems = ldm * (static_cast<int64_t>(LC->n_clips) + cts->extra_pieces);  // one row per column segment
+
+  jegal_layout::CTileSet* cts = nullptr;
+  int rc = get_ctiles(ctx, LC, width, col_op == row_op ? kPlanAllowSplit : 0, stream, &cts);
+  // A max-then-mean pooling cannot combine the pieces of a column clip longer than the tile after the
+  // row reduction; the two-pass mode can (its second pass sees the per-row values of every piece).
+  const bool need_two_pass = rc == JEGAL_ERR_UNSUPPORTED && col_op != row_op;
+  const std::string unsupported_why = need_two_pass ? ctx->err : std::string();
+  if (rc != JEGAL_OK && !need_two_pass) return rc;
+
   bool two_pass = false;
-  {
-    const int mode = env_int("JEGAL_ROWMAT", -1);
+  int64_t ws_elems = 0;
+  if (!dense && rowmat_mode != 0 && (rowmat_mode == 1 || need_two_pass || many_short)) {
+    jegal_layout::CTileSet* cts2 = nullptr;
+    rc = get_ctiles(ctx, LC, width, kPlanAllowSplit | kPlanCutHalves, stream, &cts2);
+    if (rc != JEGAL_OK) return rc;
+    ws_elems = ldm * (static_cast<int64_t>(LC->n_clips) + cts2->extra_pieces);  // one row per column segment
     const int64_t max_bytes = static_cast<int64_t>(env_int("JEGAL_ROWMAT_MAX_MB", 1024)) << 20;
-    const bool fits = ws_elems * 4 <= max_bytes && ldm < (1ll << 31) && !p.dense;
-    // auto: column clips shorter than 48 rows on average (>= ~5.3 segments per 256-column tile)
-    const bool many_short = LC->rows < static_cast<int64_t>(48) * LC->n_clips;
-    two_pass = fits && (mode == 1 || (mode != 0 && need_two_pass) || (mode < 0 && many_short));
-  }
-  if (two_pass) {
-    if (ctx->rowmat_ws_elems < static_cast<size_t>(ws_elems)) {
+    two_pass = ws_elems * 4 <= max_bytes && ldm < (1ll << 31);
+    if (two_pass && ctx->rowmat_ws_elems < static_cast<size_t>(ws_elems)) {
       if (ctx->rowmat_ws) {
         JEGAL_CUDA_OK(ctx, cudaStreamSynchronize(stream));
         cudaFree(ctx->rowmat_ws);
@@ -417,11 +401,38 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
         ctx->rowmat_ws_elems = static_cast<size_t>(ws_elems);
       }
     }
+    if (two_pass) cts = cts2;
   }
   if (need_two_pass && !two_pass)
     return set_err(ctx, JEGAL_ERR_UNSUPPORTED,
                    unsupported_why + " in one pass; the two-pass mode needs a workspace of " +
-                       std::to_string((ws_elems * 4) >> 20) + " MB (JEGAL_ROWMAT_MAX_MB, JEGAL_ROWMAT)");
+                       std::to_string((ldm * (static_cast<int64_t>(LC->n_clips) + 8) * 4) >> 20) +
+                       "+ MB (JEGAL_ROWMAT_MAX_MB, JEGAL_ROWMAT)");
+
+  SimpoolParams p{};
+  p.ctiles = cts->dev;
+  p.n_ctiles = cts->n;
+  p.n_rtiles = static_cast<int32_t>((LR->rows + width - 1) / width);
+  // L2 plan: DRAM traffic of a launch = R once + (#phases) x C, because a column tile has no reuse
+  // inside a phase; so phases of R are made as large as stays L2-resident while every cluster
+  // re-streams them, and column tiles are fetched with evict_first so they do not displace R.
+  p.c_policy = env_int("JEGAL_C_POLICY", 2);
+  const int64_t chunk_bytes = static_cast<int64_t>(env_int("JEGAL_CHUNK_MB", 24)) << 20;
+  p.chunk_rtiles = static_cast<int32_t>(std::max<int64_t>(1, chunk_bytes / (static_cast<int64_t>(width) * kD * 2)));
+  p.n_rows_R = static_cast<int32_t>(LR->rows);
+  p.rowinfo_R = LR->rowinfo_dev;
+  p.uni_len_R = LR->uniform_len;
+  p.dense = dense ? 1 : 0;
+  p.cu_R = LR->cu_dev;
+  p.cu_C = LC->cu_dev;
+  p.rscale = cols_are_gest ? cscale_dev : gscale_dev;
+  p.cscale = cols_are_gest ? gscale_dev : cscale_dev;
+  p.out = scores_dev;
+  p.ld_r = cols_are_gest ? ld_c : ld_g;
+  p.ld_c = cols_are_gest ? ld_g : ld_c;
+  p.idesc = ptx::make_idesc_f16(op_dtype == JEGAL_BF16 ? 1u : 0u, static_cast<uint32_t>(width),
+                                static_cast<uint32_t>(width));
+
   const int final_row_op = row_op;
   if (two_pass) {
     p.out = ctx->rowmat_ws;

@@ -83,10 +83,11 @@ struct jegal_layout {
   int32_t uniform_len = 0;      // > 0 when all clips have the same length
   struct CTileSet {
     int width = 0;
-    bool allow_split = false;
+    int flags = 0;  // kPlanAllowSplit | kPlanCutHalves
     bool any_partial = false;
-    int32_t extra_pieces = 0;      // segments - clips (pieces of split clips beyond the first)
-    int32_t* seg_dev = nullptr;    // any_partial only: [n_clips + 1] first segment number of every clip
+    int32_t extra_pieces = 0;      // segments - clips (pieces of split clips, half-tile cuts)
+    std::vector<int32_t> seg_host; // [n_clips + 1] first segment number of every clip
+    int32_t* seg_dev = nullptr;    // uploaded when extra_pieces > 0
     int n = 0;
     std::vector<jegal::CTile> host;
     jegal::CTile* dev = nullptr;
@@ -141,7 +142,10 @@ int make_operand_tmap(jegal_ctx* ctx, CUtensorMap* out, const void* rows_dev, in
 // Pure host logic (unit-tested without a GPU): pack whole clips greedily into column tiles of
 // `width` rows; clips longer than `width` are cut into partial tiles when `allow_split`.
 // Returns JEGAL_OK, or JEGAL_ERR_UNSUPPORTED with *bad_clip set.
-int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, bool allow_split,
-                      std::vector<CTile>* out, bool* any_partial, int32_t* bad_clip);
+// kPlanCutHalves: additionally no segment crosses column width/2 (a clip that would is cut there).
+// seg_of_clip (nullable): [n_clips + 1] number of every clip's first segment.
+constexpr int kPlanAllowSplit = 1, kPlanCutHalves = 2;
+int plan_column_tiles(const int32_t* cu, int32_t n_clips, int width, int flags, std::vector<CTile>* out,
+                      bool* any_partial, int32_t* bad_clip, std::vector<int32_t>* seg_of_clip);
 
 }  // namespace jegal

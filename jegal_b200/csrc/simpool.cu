@@ -352,7 +352,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(t_full(b), 1);
-      mbar_init(t_empty(b), 4 * kCG);  // one arrival per epilogue warp of every CTA
+      // one arrival per epilogue warp that drains the buffer, in every CTA (two-pass mode: both warpgroups)
+      mbar_init(t_empty(b), (kRowOp == OP_NONE ? 4 * kEpiGroups : 4) * kCG);
     }
     fence_mbar_init();
   }
@@ -479,8 +480,15 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue
+    // Fused modes: warpgroup g drains accumulator buffer g (every other tile).  Then tile i+2 can only be
+    // computed once tile i is pooled, so the tensor pipe stays busy iff T_epilogue(tile) <= T_mma(tile).
+    // Two-pass mode (kRowOp == OP_NONE): BOTH warpgroups drain EVERY tile, warpgroup g the columns
+    // [g * N/2, (g + 1) * N/2) -- a buffer is held for half the time (T_epilogue / 2 <= T_mma).  The plan cuts
+    // every segment at N/2 (kPlanCutHalves), so the halves are independent: no carry, no synchronisation.
+    constexpr bool kSplit = kRowOp == OP_NONE;
+    constexpr int kHalfChunks = UMMA_N / 64;       // 32-column chunks per half tile
     const int q = (warp - kEpiWarp0) & 3;          // TMEM lane quarter == warp % 4
-    const uint32_t grp = (warp - kEpiWarp0) >> 2;  // this warpgroup drains accumulator buffer `grp`
+    const uint32_t grp = (warp - kEpiWarp0) >> 2;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     UnitIter it(p, cluster, nclusters);
     int32_t ct, rt0, nrt;
@@ -493,13 +501,17 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
       const int32_t clip0 = __ldg(&ctile->clip0);
       const int32_t part = __ldg(&ctile->partial);
       const bool col_partial = (part & 1) != 0;
-      const int32_t seg0 = clip0 + (part >> 1);  // two-pass mode: M row of the tile's first segment
       const uint32_t my_em = lane < 8 ? __ldg(&ctile->endmask[lane]) : 0u;
       const int nchunks = (n_valid + 31) >> 5;
+      const int ch_lo = kSplit ? static_cast<int>(grp) * kHalfChunks : 0;
+      const int ch_hi = kSplit ? min(nchunks, ch_lo + kHalfChunks) : nchunks;
+      // two-pass mode: M row of this warpgroup's first segment (segments left of the split belong to group 0)
+      int32_t seg0 = clip0 + (part >> 1);
+      if (kSplit && grp != 0) seg0 += __reduce_add_sync(0xffffffffu, lane < kHalfChunks ? __popc(my_em) : 0);
       int4 ri_next = make_int4(-1, 0, 1, 0);
       bool have_next = false;
       for (int32_t t = 0; t < nrt; ++t, ++tile) {
-        if ((tile & 1u) != grp) continue;  // the other warpgroup owns this tile
+        if (!kSplit && (tile & 1u) != grp) continue;  // fused modes: the other warpgroup owns this tile
         // per-row context for this tile.  Ragged row side: the {clip, begin, end} record of this
         // thread's row was requested while the previous own tile was being pooled (software
         // pipelining: the L2 round trip was 23 % of the epilogue's time when issued here).
@@ -548,7 +560,7 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
           rc.flags = fl;
           rc.out_row = p.out + static_cast<int64_t>(rc.rclip) * p.ld_r;
         }
-        const uint32_t buf = grp;
+        const uint32_t buf = tile & 1u;
         JEGAL_TRACED(0, mbar_wait(t_full(buf), (tile >> 1) & 1u));
         tc_fence_after();
         const long long t_pool0 = p.trace ? clock64() : 0;
@@ -570,23 +582,27 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
         float acc = op_ident<kColOp>();
         int32_t cclip = clip0;
         float* m_ptr = rc.out_row + static_cast<int64_t>(seg0) * p.ld_c;  // two-pass mode: &M[seg0][row]
+        if (ch_lo >= ch_hi) {  // two-pass mode, narrow tile: nothing in the right half
+          release();
+          continue;
+        }
         uint32_t va[32], vb[32];  // two chunks in flight: load c+1 while chunk c is pooled
-        tmem_ld_32x32(t_addr, va);
-        for (int ch = 0; ch < nchunks; ch += 2) {
+        tmem_ld_32x32(t_addr + ch_lo * 32, va);
+        for (int ch = ch_lo; ch < ch_hi; ch += 2) {
           // every lane holds the same end mask; the ballot tells the compiler so (uniform registers)
           const uint32_t em_a = __ballot_sync(0xffffffffu, (__shfl_sync(0xffffffffu, my_em, ch) >> lane) & 1u);
           const uint32_t em_b = __ballot_sync(0xffffffffu, (__shfl_sync(0xffffffffu, my_em, ch + 1) >> lane) & 1u);
           tmem_ld_wait();
-          if (ch + 1 < nchunks) tmem_ld_32x32(t_addr + (ch + 1) * 32, vb);
+          if (ch + 1 < ch_hi) tmem_ld_32x32(t_addr + (ch + 1) * 32, vb);
           else release();
           if constexpr (kDense) {
             store_chunk_dense(va, n_valid - ch * 32, clip0 + ch * 32, rc, p);
           } else {
             pool_chunk<kColOp, kRowOp>(va, em_a, acc, cclip, m_ptr, rc, p);
           }
-          if (ch + 1 < nchunks) {
+          if (ch + 1 < ch_hi) {
             tmem_ld_wait();
-            if (ch + 2 < nchunks) tmem_ld_32x32(t_addr + (ch + 2) * 32, va);
+            if (ch + 2 < ch_hi) tmem_ld_32x32(t_addr + (ch + 2) * 32, va);
             else release();
             if constexpr (kDense) {
               store_chunk_dense(vb, n_valid - (ch + 1) * 32, clip0 + (ch + 1) * 32, rc, p);
@@ -680,61 +696,101 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float value)
   for (int64_t i = (n4 << 2) + i0; i < n; i += stride) dst[i] = value;
 }
 
-// Pass 2 of the two-pass mode.  One warp per (row clip, kRrCols consecutive column clips): the lanes
-// stride over the clip's rows of M[c] (contiguous, coalesced; kRrCols independent streams in flight), a
-// butterfly finishes each reduction, lanes 0..kRrCols-1 write the scores.  The 8 warps of a block take
-// 8 * kRrCols consecutive column clips of one row clip.
-constexpr int kRrCols = 4;
+// Pass 2 of the two-pass mode.  A block takes ONE column clip c and kRrClips = 64 consecutive row clips, a
+// warp 8 consecutive row clips: together the 8 warps stream one contiguous stretch of M[c] (row clips are
+// contiguous row ranges), so DRAM sees long sequential reads.  The warp walks its 8 clips in lock step --
+// step k loads rows begin_j + 32k + lane of every clip j, 8 independent coalesced loads in flight per lane --
+// then 8 interleaved butterflies finish the reductions and lanes 0..7 write the scores.  The pieces of a
+// split / half-cut column clip (rows seg_C[c] .. seg_C[c+1] of M) are combined per row with the column
+// operation first.
+constexpr int kRrClips = 64;
 template <int kColOp, int kRowOp>
 __global__ void __launch_bounds__(256)
 rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __restrict__ cu_R, int32_t n_rclips,
                  const int32_t* __restrict__ cu_C, const int32_t* __restrict__ seg_C, int32_t n_cclips,
-                 int32_t cgroups, const float* __restrict__ rscale, const float* __restrict__ cscale,
+                 int32_t rblocks, const float* __restrict__ rscale, const float* __restrict__ cscale,
                  float* __restrict__ out, int64_t ld_r, int64_t ld_c) {
-  const int lane = threadIdx.x & 31;
-  const int64_t b = blockIdx.x;
-  const int32_t r = static_cast<int32_t>(b / cgroups);
-  const int32_t c0 = (static_cast<int32_t>(b - static_cast<int64_t>(r) * cgroups) * 8 + (threadIdx.x >> 5)) * kRrCols;
-  if (c0 >= n_cclips) return;
-  const int32_t r0 = __ldg(cu_R + r), r1 = __ldg(cu_R + r + 1);
-  float v[kRrCols];
-  if (seg_C == nullptr) {  // one M row per column clip
-    const float* src[kRrCols];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t c = static_cast<int32_t>(blockIdx.x / rblocks);
+  const int32_t ra = static_cast<int32_t>(blockIdx.x - static_cast<int64_t>(c) * rblocks) * kRrClips + warp * 8;
+  if (ra >= n_rclips) return;
+  const int32_t m0 = seg_C ? __ldg(seg_C + c) : c;
+  const int32_t np = seg_C ? __ldg(seg_C + c + 1) - m0 : 1;
+  const float* src = M + static_cast<int64_t>(m0) * ldm;
+  // clip boundaries of this warp: lane l holds cu_R[min(ra + l, n_rclips)], broadcast into registers
+  const int32_t my_b = __ldg(cu_R + min(ra + min(lane, 8), n_rclips));
+  int32_t bnd[9];
 #pragma unroll
-    for (int j = 0; j < kRrCols; ++j) {
-      v[j] = op_ident<kRowOp>();
-      src[j] = M + static_cast<int64_t>(min(c0 + j, n_cclips - 1)) * ldm;
+  for (int j = 0; j < 9; ++j) bnd[j] = __shfl_sync(0xffffffffu, my_b, j);
+  int32_t longest = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) longest = max(longest, bnd[j + 1] - bnd[j]);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = op_ident<kRowOp>();
+  if (np == 1) {
+    // One 16-byte load per lane covers 128 rows of a clip per step; 8 clips in lock step = 4 KB in flight per
+    // warp and round trip to DRAM (with 4-byte loads the kernel sat at 2.6 TB/s: too few bytes in flight).
+    // Loads start at the 16-byte boundary below the clip; elements outside [begin, end) are masked by select.
+    const float4* ptr[8];
+    int32_t lo[8], hi[8];  // this lane's float4 holds rows lo..hi-1 (relative to its first element) of clip j
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int32_t a = bnd[j] & ~3;
+      ptr[j] = reinterpret_cast<const float4*>(src + a) + lane;
+      lo[j] = bnd[j] - a - 4 * lane;
+      hi[j] = bnd[j + 1] - a - 4 * lane;
     }
-    for (int32_t i = r0 + lane; i < r1; i += 32) {
+    for (int32_t k = 0; k < longest + 3; k += 128) {
+      float4 x[8];
 #pragma unroll
-      for (int j = 0; j < kRrCols; ++j) v[j] = op_apply<kRowOp>(v[j], __ldcs(src[j] + i));
+      for (int j = 0; j < 8; ++j) {
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hi[j] > 0) x[j] = __ldcs(ptr[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float id = op_ident<kRowOp>();
+        const float e0 = (lo[j] <= 0 && hi[j] > 0) ? x[j].x : id;
+        const float e1 = (lo[j] <= 1 && hi[j] > 1) ? x[j].y : id;
+        const float e2 = (lo[j] <= 2 && hi[j] > 2) ? x[j].z : id;
+        const float e3 = (lo[j] <= 3 && hi[j] > 3) ? x[j].w : id;
+        v[j] = op_apply<kRowOp>(v[j], op_apply<kRowOp>(op_apply<kRowOp>(e0, e1), op_apply<kRowOp>(e2, e3)));
+        ptr[j] += 32;
+        lo[j] -= 128;
+        hi[j] -= 128;
+      }
     }
-  } else {  // split column clips: combine the pieces of a clip per row (col_op) before reducing over rows
+  } else {
+    for (int32_t k = lane; k < longest; k += 32) {
 #pragma unroll
-    for (int j = 0; j < kRrCols; ++j) {
-      v[j] = op_ident<kRowOp>();
-      const int32_t c = min(c0 + j, n_cclips - 1);
-      const int32_t m0 = __ldg(seg_C + c), m1 = __ldg(seg_C + c + 1);
-      for (int32_t i = r0 + lane; i < r1; i += 32) {
-        float x = op_ident<kColOp>();
-        for (int32_t m = m0; m < m1; ++m) x = op_apply<kColOp>(x, __ldcs(M + static_cast<int64_t>(m) * ldm + i));
-        v[j] = op_apply<kRowOp>(v[j], x);
+      for (int j = 0; j < 8; ++j) {
+        const int32_t i = bnd[j] + k;
+        if (i < bnd[j + 1]) {
+          float x = __ldcs(src + i);
+          for (int32_t m = 1; m < np; ++m) x = op_apply<kColOp>(x, __ldcs(src + static_cast<int64_t>(m) * ldm + i));
+          v[j] = op_apply<kRowOp>(v[j], x);
+        }
       }
     }
   }
 #pragma unroll
   for (int k = 16; k > 0; k >>= 1) {
 #pragma unroll
-    for (int j = 0; j < kRrCols; ++j) v[j] = op_apply<kRowOp>(v[j], __shfl_xor_sync(0xffffffffu, v[j], k));
+    for (int j = 0; j < 8; ++j) v[j] = op_apply<kRowOp>(v[j], __shfl_xor_sync(0xffffffffu, v[j], k));
   }
   float mine = v[0];
+  int32_t len = bnd[1] - bnd[0];
 #pragma unroll
-  for (int j = 1; j < kRrCols; ++j) mine = lane == j ? v[j] : mine;
-  const int32_t c = c0 + lane;
-  if (lane < kRrCols && c < n_cclips) {
-    float sc = (rscale ? __ldg(rscale + r) : 1.0f) * (cscale ? __ldg(cscale + c) : 1.0f);
-    if constexpr (kRowOp == OP_SUM) sc *= 1.0f / static_cast<float>(r1 - r0);
+  for (int j = 1; j < 8; ++j) {
+    mine = lane == j ? v[j] : mine;
+    len = lane == j ? bnd[j + 1] - bnd[j] : len;
+  }
+  const int32_t r = ra + lane;
+  if (lane < 8 && r < n_rclips) {
+    float sc = (cscale ? __ldg(cscale + c) : 1.0f) * (rscale ? __ldg(rscale + r) : 1.0f);
     if constexpr (kColOp == OP_SUM) sc *= 1.0f / static_cast<float>(__ldg(cu_C + c + 1) - __ldg(cu_C + c));
+    if constexpr (kRowOp == OP_SUM) sc *= 1.0f / static_cast<float>(len);
     out[static_cast<int64_t>(r) * ld_r + static_cast<int64_t>(c) * ld_c] = mine * sc;
   }
 }
@@ -745,8 +801,8 @@ int launch_rowreduce(jegal_ctx* ctx, const float* M, int64_t ldm, const int32_t*
                      const int32_t* cu_C, const int32_t* seg_C, int32_t n_cclips, int col_op, int row_op,
                      const float* rscale, const float* cscale, float* out, int64_t ld_r, int64_t ld_c,
                      cudaStream_t stream) {
-  const int32_t cgroups = (n_cclips + 8 * kRrCols - 1) / (8 * kRrCols);
-  const int64_t blocks = static_cast<int64_t>(n_rclips) * cgroups;
+  const int32_t cgroups = (n_rclips + kRrClips - 1) / kRrClips;  // blocks per column clip
+  const int64_t blocks = static_cast<int64_t>(n_cclips) * cgroups;
   if (blocks <= 0) return JEGAL_OK;
   if (blocks > 0x7fffffff) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "rowreduce: more than 2^31 blocks");
   const unsigned g = static_cast<unsigned>(blocks);

@@ -162,6 +162,38 @@ def _check_plan(lengths, width, allow_split):
     assert next_clip == len(lengths) and (covered == 1).all()
 
 
+def test_column_tile_planner_half_cuts():
+    """flags = 3 (allow split + cut halves, the two-pass plan): no segment crosses column width/2, segments are
+    numbered in tile order, and every clip is covered exactly once by its pieces."""
+    rng = np.random.default_rng(1)
+    for width in (128, 256):
+        h = width // 2
+        for _ in range(40):
+            n = int(rng.integers(1, 60))
+            lengths = rng.integers(1, 90, n)
+            lengths = np.where(rng.random(n) < 0.1, rng.integers(width + 1, 3 * width, n), lengths)
+            rc, nt, tiles = _plan(lengths, width, 3)
+            assert rc == 0
+            cu = np.concatenate([[0], np.cumsum(lengths)])
+            covered = np.zeros(cu[-1], dtype=np.int32)
+            next_seg, pieces = 0, np.zeros(n, dtype=np.int32)
+            for t in tiles:
+                row0, n_valid, clip0, part = (int(x) for x in t[:4])
+                assert clip0 + (part >> 1) == next_seg
+                ends = [c * 32 + j for c in range(8) for j in range(32) if (int(t[4 + c]) >> j) & 1]
+                assert ends[-1] == n_valid - 1 and (n_valid <= h or (h - 1) in ends)
+                start = 0
+                for e in ends:  # every segment lies inside one clip and one half of the tile
+                    c = int(np.searchsorted(cu, row0 + start, side="right") - 1)
+                    assert cu[c] <= row0 + start and row0 + e + 1 <= cu[c + 1]
+                    assert (start < h) == (e < h)
+                    pieces[c] += 1
+                    covered[row0 + start: row0 + e + 1] += 1
+                    start = e + 1
+                next_seg += len(ends)
+            assert (covered == 1).all() and (pieces >= 1).all() and next_seg == pieces.sum()
+
+
 def test_column_tile_planner_properties():
     rng = np.random.default_rng(0)
     for width in (128, 256):
