@@ -148,7 +148,7 @@ def run_cpu_sample(wl: dict, g_sample: int, steps: int, warmup: int):
 def main_reference(args, wl, rank, world):
     if rank != 0:
         return
-    g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 1024))
+    g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 4096))
     cores = os.cpu_count() or 1
     value, dt = run_cpu_sample(wl, g_sample, args.steps, args.warmup)
     sample = (f"{wl['Q']} queries x {g_sample} gallery clips per step (same T/W/D/pooling/top-k), "
@@ -337,7 +337,7 @@ def main_ours(args, wl, rank, local_rank, world):
                      "traffic_unit": "bytes (dram read+write per launch, ncu; profiles/k1_traffic_r01.json)"},
     }
     if world == 1 and not args.no_cpu:
-        g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 1024))
+        g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 4096))
         n_rep = 3
         cv, cdt = run_cpu_sample(wl, g_sample, n_rep, 1)
         line["cpu_baseline"] = {
