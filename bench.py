@@ -264,11 +264,11 @@ def main_ours(args, wl, rank, local_rank, world):
     d2h = Q * k * 8
 
     def e2e_step():
-        q_dev = None
-        if world > 1:
-            q_dev = q_host.to(dev, non_blocking=True) if rank == 0 else torch.empty((Q * T, 512), dtype=torch.float16, device=dev)
-            dist.broadcast(q_dev, src=0)
-        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_dev=q_dev)
+        # queries start in rank 0's pinned host memory; they are copied (and with several GPUs broadcast) in 4
+        # parts, pipelined with the scoring of the first gallery chunk (jegal_b200.streaming)
+        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode,
+                                                  q_parts=4,
+                                                  bcast_src=0 if world > 1 else None)
         if world > 1:
             vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
             idxs = torch.empty((world * Q, k), dtype=torch.int32, device=dev)
@@ -327,7 +327,7 @@ def main_ours(args, wl, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(te[0]) * 1e3, "steps": e2e_steps,
-                "path": "pinned host fp16 embeddings -> chunked H2D overlapped with K0/K1/K2 per chunk -> merge -> top-k (values, indices) -> host (jegal_b200.streaming.retrieve_topk_streamed)"},
+                "path": "pinned host fp16 embeddings -> chunked H2D (gallery chunks; with N > 1 also query parts, broadcast from rank 0) overlapped with K0/K1/K2 -> merge -> top-k (values, indices) -> host (jegal_b200.streaming.retrieve_topk_streamed)"},
         "gpu_launches": int(lc[0]),
         "roofline": {"bound": "tensor", "kernel": "simpool_kernel (K1)", "achieved": achieved, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],

@@ -21,7 +21,7 @@ class StreamedGallery:
     """Pinned host gallery (packed fp16/fp32 rows + per-clip lengths) cut into clip-aligned chunks."""
 
     def __init__(self, rows_host: torch.Tensor, lengths: np.ndarray, chunk_clips: int = 8192, device=None,
-                 idx_base: int = 0):
+                 idx_base: int = 0, ramp: bool = True):
         if rows_host.is_cuda or rows_host.dim() != 2 or rows_host.shape[1] != 512:
             raise JegalError("StreamedGallery: rows_host must be a host [rows, 512] tensor")
         self.rows = rows_host if rows_host.is_pinned() else rows_host.pin_memory()
@@ -29,10 +29,17 @@ class StreamedGallery:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.idx_base = idx_base
         cu = np.concatenate([[0], np.cumsum(self.lengths)])
+        # Scoring cannot start before the first chunk has arrived, so the first chunks are small and grow
+        # geometrically (chunk_clips / 8, / 8, / 4, / 2, then full size): the start-up latency is the copy of
+        # 1/8 chunk instead of a whole one, and the small launches at the start cost little.
         self.chunks = []
-        for lo in range(0, len(self.lengths), chunk_clips):
-            hi = min(lo + chunk_clips, len(self.lengths))
+        sizes = [max(1, chunk_clips // d) for d in (8, 8, 4, 2)] if ramp and chunk_clips >= 64 else []
+        lo = 0
+        while lo < len(self.lengths):
+            size = sizes.pop(0) if sizes else chunk_clips
+            hi = min(lo + size, len(self.lengths))
             self.chunks.append((lo, hi, int(cu[lo]), int(cu[hi]), ops.Layout.from_lengths(self.lengths[lo:hi])))
+            lo = hi
         max_rows = max((c[3] - c[2] for c in self.chunks), default=0)
         self.stage = [torch.empty((max_rows, 512), dtype=self.rows.dtype, device=self.dev) for _ in range(2)]
         self.op16 = [torch.empty((max_rows, 512), dtype=torch.bfloat16, device=self.dev) for _ in range(2)]
@@ -46,20 +53,66 @@ class StreamedGallery:
         return self.rows.numel() * self.rows.element_size()
 
 
+def _query_parts(q_layout: ops.Layout, n_parts: int):
+    """Contiguous clip ranges of the query set: (clip_lo, clip_hi, row_lo, row_hi, layout) per part."""
+    lengths = np.asarray(q_layout.lengths, dtype=np.int64)
+    nq = len(lengths)
+    n_parts = max(1, min(int(n_parts), nq)) if nq else 1
+    cache = q_layout.__dict__.setdefault("_query_parts_cache", {})  # layouts own device tables: build once
+    if n_parts in cache:
+        return cache[n_parts]
+    cu = np.concatenate([[0], np.cumsum(lengths)])
+    per = (nq + n_parts - 1) // n_parts if nq else 0
+    parts = []
+    for lo in range(0, nq, max(per, 1)):
+        hi = min(lo + per, nq)
+        parts.append((lo, hi, int(cu[lo]), int(cu[hi]), q_layout if (lo == 0 and hi == nq) else ops.Layout.from_lengths(lengths[lo:hi])))
+    cache[n_parts] = parts
+    return parts
+
+
 def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: StreamedGallery, k: int = 10,
                            mode: str = "max_t_mean_w", queries_are: str = "gesture",
-                           q_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                           q_dev: Optional[torch.Tensor] = None, q_parts: int = 1,
+                           bcast_src: Optional[int] = None, group=None,
+                           q_dtype: torch.dtype = torch.float16) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery clips per query; queries and gallery start in (pinned) host memory.
     Returns DEVICE tensors (values [Q, k], global indices [Q, k]); call .cpu() to finish the round trip.
-    ``q_dev`` may carry queries that are already on the device (e.g. after a broadcast)."""
+    ``q_dev`` may carry queries that are already on the device (e.g. after a broadcast).
+
+    ``q_parts`` > 1 pipelines the QUERY side too: the query clips are cut into contiguous parts, part p+1
+    is copied (and, with ``bcast_src`` set in a torch.distributed job, broadcast from that rank over NCCL)
+    while part p is being scored against the first gallery chunk, so scoring starts after 1/q_parts of the
+    query transfer instead of all of it.  On every rank but ``bcast_src`` ``q_host`` may be None (its dtype
+    is then ``q_dtype``)."""
     dev = gallery.dev
     main = torch.cuda.current_stream(dev)
-    if q_dev is None:
-        q_dev = q_host.to(dev, non_blocking=True)
-    q16, _ = ops.prep(q_dev, q_layout)
     nq = q_layout.n_clips
     if not gallery.chunks:
         return (torch.full((nq, k), float("-inf"), device=dev), torch.full((nq, k), -1, dtype=torch.int32, device=dev))
+    import torch.distributed as dist
+
+    bcast = bcast_src is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    parts = _query_parts(q_layout, q_parts if q_dev is None else 1)
+    ready = [None] * len(parts)  # per part: a CUDA event (copy) or an NCCL work handle (broadcast)
+    if q_dev is None:
+        i_am_src = (not bcast) or dist.get_rank(group) == bcast_src
+        q_dtype = q_host.dtype if q_host is not None else q_dtype
+        q_dev = torch.empty((q_layout.rows, 512), dtype=q_dtype, device=dev)
+        if not hasattr(gallery, "q_stream"):
+            gallery.q_stream = torch.cuda.Stream(device=dev)
+        gallery.q_stream.wait_stream(main)  # q_dev was allocated on main
+        with torch.cuda.stream(gallery.q_stream):
+            for p, (lo, hi, r0, r1, _) in enumerate(parts):
+                if i_am_src:
+                    q_dev[r0:r1].copy_(q_host[r0:r1], non_blocking=True)
+                if bcast:  # enqueued behind the copy; the next part's copy does not wait for it
+                    ready[p] = dist.broadcast(q_dev[r0:r1], src=bcast_src, group=group, async_op=True)
+                else:
+                    ready[p] = torch.cuda.Event()
+                    ready[p].record(gallery.q_stream)
+        q_dev.record_stream(gallery.q_stream)
+    q16 = torch.empty((q_layout.rows, 512), dtype=torch.bfloat16, device=dev)
     vals = torch.empty((len(gallery.chunks), nq, k), dtype=torch.float32, device=dev)
     idxs = torch.empty((len(gallery.chunks), nq, k), dtype=torch.int32, device=dev)
 
@@ -81,13 +134,24 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
         g16 = gallery.op16[b][: r1 - r0]
         ops.prep(gallery.stage[b][: r1 - r0], lay, out=g16)
         gallery.consumed[b].record(main)
-        if queries_are == "gesture":
-            s = ops.simpool_allpairs(q16, q_layout, g16, lay, mode)
-        else:
-            s = ops.simpool_allpairs(g16, lay, q16, q_layout, mode, content_major=True)
-        v, i = ops.topk(s, k, idx_offset=gallery.idx_base + lo)
-        vals[c].copy_(v)
-        idxs[c].copy_(i)
+        # the query parts only matter while they are still arriving: the first gallery chunk is scored part
+        # by part, every later chunk against the whole query set in one launch
+        todo = parts if c == 0 else [(0, nq, 0, q_layout.rows, q_layout)]
+        for p, (qlo, qhi, qr0, qr1, qlay) in enumerate(todo):
+            if c == 0:  # first use of this query part: wait for its transfer, normalise + cast it
+                if ready[p] is not None:
+                    if isinstance(ready[p], torch.cuda.Event):
+                        main.wait_event(ready[p])
+                    else:
+                        ready[p].wait()
+                ops.prep(q_dev[qr0:qr1], qlay, out=q16[qr0:qr1])
+            if queries_are == "gesture":
+                s = ops.simpool_allpairs(q16[qr0:qr1], qlay, g16, lay, mode)
+            else:
+                s = ops.simpool_allpairs(g16, lay, q16[qr0:qr1], qlay, mode, content_major=True)
+            v, i = ops.topk(s, k, idx_offset=gallery.idx_base + lo)
+            vals[c, qlo:qhi].copy_(v)
+            idxs[c, qlo:qhi].copy_(i)
     if len(gallery.chunks) == 1:
         return vals[0], idxs[0]
     return ops.topk_merge(vals, idxs)

@@ -428,6 +428,23 @@ def test_streamed_retrieval_equals_resident(dev):
     assert np.array_equal(i[:, 0].cpu().numpy(), gt)
 
 
+def test_streamed_retrieval_with_query_parts_equals_resident(dev):
+    """The query side pipelined in parts (copy of part p+1 overlaps scoring of part p) returns the same lists."""
+    from jegal_b200 import ops, streaming
+    rng = np.random.default_rng(31)
+    q = [x for x in rand_clips(23, 20, 70, 32)]
+    g = [x for x in rand_clips(301, 4, 20, 33)]
+    q_rows = torch.from_numpy(np.concatenate(q)).pin_memory()
+    ql = ops.Layout.from_lengths([len(x) for x in q])
+    gal = streaming.StreamedGallery(torch.from_numpy(np.concatenate(g)), np.array([len(x) for x in g]), chunk_clips=64,
+                                    device=dev)
+    v1, i1 = streaming.retrieve_topk_streamed(q_rows, ql, gal, k=5)
+    for parts in (2, 5, 64):
+        v2, i2 = streaming.retrieve_topk_streamed(q_rows, ql, gal, k=5, q_parts=parts)
+        # same pair scores up to the order of the cross-warp atomic adds; same lists
+        assert torch.equal(i1, i2) and (v1 - v2).abs().max() < 1e-6, parts
+
+
 def test_topk_exchange_single_rank(dev):
     """World-size-1 exchange (self slot only) == plain K2: covers the fused kernels and the flag protocol."""
     from jegal_b200 import ops
