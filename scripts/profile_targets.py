@@ -10,7 +10,7 @@ import torch
 from jegal_b200 import ops, synth
 
 dev = torch.device("cuda:0")
-which = set((sys.argv[1] if len(sys.argv) > 1 else "k0,k1,k2,k3,k4").split(","))
+which = set((sys.argv[1] if len(sys.argv) > 1 else "k0,k1,k2,k3,k4,k5,k1cfg2").split(","))
 reps = int(os.environ.get("PROFILE_REPS", 2))
 
 if which & {"k0", "k1", "k2"}:
@@ -36,6 +36,14 @@ if "k3" in which:
     hi = torch.full((cs.n,), 1000, dtype=torch.int32, device=dev)
     for _ in range(reps):
         ops.spot(g16, gl, c16, cl, wi, win_lo=lo, win_hi=hi)
+    if "k5" in which:  # word-level mean pooling at the same clip shapes: every word = mean of its frames (D = 256 fp16)
+        import numpy as np
+        feats = torch.randn(gl.rows, 256, device=dev).half()
+        sb = torch.from_numpy(np.concatenate([cs.cu_t[i] + np.asarray([b[1] for b in cs.boundaries[i]]) for i in range(cs.n)]).astype(np.int32)).to(dev)
+        se = torch.from_numpy(np.concatenate([cs.cu_t[i] + np.asarray([b[2] + 1 for b in cs.boundaries[i]]) for i in range(cs.n)]).astype(np.int32)).to(dev)
+        se = torch.minimum(se, torch.tensor(gl.rows, dtype=torch.int32, device=dev))
+        for _ in range(reps):
+            ops.segment_mean(feats, sb, se)
 if "k4" in which:
     ds = synth.cfg4_asd(10000, 4, device=dev)
     cs = ds.clips
