@@ -69,7 +69,7 @@ def main():
     t_gpu, _ = best(lambda: scoring.spot_batch(gest, cont, tw, windows=win))
     out.append({"config": "cfg3 AVS-Spot 20000 clips: heatmap row + argmax + decision (CPU: 2000-clip loop scaled x10)",
                 "cpu_s": t_cpu * 10, "gpu_s": t_gpu, "speedup": t_cpu * 10 / t_gpu, "cores": cores,
-                "note": "GPU time includes packing 20000 numpy clips on the host and the H2D copy"})
+                "note": "GPU time includes packing 20000 numpy clips on the host (several threads) and the H2D copy"})
     # ---- config 4: ASD, 10000 groups x 4 tracks
     ds = synth.cfg4_asd(10000, 4)
     cs = ds.clips
@@ -85,7 +85,7 @@ def main():
     t_gpu, _ = best(lambda: scoring.asd_batch(cont, gest, ds.pair_gest, ds.pair_cont, 4, prefixes=(4,)))
     out.append({"config": "cfg4 AVS-Asd 10000 groups x 4 tracks: cosine of mean-pooled clips + argmax (CPU: 2000 groups scaled x5)",
                 "cpu_s": t_cpu * 5, "gpu_s": t_gpu, "speedup": t_cpu * 5 / t_gpu, "cores": cores,
-                "note": "GPU time includes packing 40000 numpy clips on the host and the H2D copy"})
+                "note": "GPU time includes packing 40000 numpy clips on the host (several threads) and the H2D copy"})
     for o in out:
         print(json.dumps(o))
 

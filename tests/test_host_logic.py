@@ -245,3 +245,19 @@ def test_heatmap_renderer_jet_blend_and_png(tmp_path):
     idat = raw[raw.index(b"IDAT") + 4: raw.index(b"IEND") - 8]
     pix = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
     assert np.array_equal(pix[0, 0], np.rint(want * 255).astype(np.uint8))
+
+
+def test_pack_rows_host_threaded_equals_concatenate():
+    from jegal_b200.scoring import pack_rows_host
+    rng = np.random.default_rng(4)
+    arrs = [rng.standard_normal((int(L), 512)).astype(np.float16) for L in rng.integers(1, 400, size=700)]
+    want = np.concatenate(arrs, axis=0)
+    out = np.zeros_like(want)
+    seen = []
+    pack_rows_host(arrs, out, threads=4, on_group=lambda r0, r1: seen.append((r0, r1)))
+    assert np.array_equal(out, want)
+    assert seen[0][0] == 0 and seen[-1][1] == len(want) and all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    small = arrs[:3]
+    out2 = np.zeros((sum(len(a) for a in small), 512), dtype=np.float16)
+    pack_rows_host(small, out2)
+    assert np.array_equal(out2, np.concatenate(small))
