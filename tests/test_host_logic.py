@@ -261,3 +261,28 @@ def test_pack_rows_host_threaded_equals_concatenate():
     out2 = np.zeros((sum(len(a) for a in small), 512), dtype=np.float16)
     pack_rows_host(small, out2)
     assert np.array_equal(out2, np.concatenate(small))
+
+
+def test_wordlevel_range_logic_against_reference_golden(golden, monkeypatch):
+    """The host half of jegal_b200.wordlevel (which rows belong to which word, invalid-sample bookkeeping)
+    against the outputs of the reference's own methods; the K5 launch is replaced by a torch mean HERE ONLY,
+    so the integer logic is covered without a GPU (the kernel itself is covered by the -m gpu suite)."""
+    import torch
+    from jegal_b200 import wordlevel
+    from jegal_testutil import wordlevel_case
+
+    def cpu_pool(emb, ranges, counts):
+        x = emb.reshape(-1, emb.shape[-1])
+        rows = [x[lo:hi].mean(dim=0) if hi - lo > 1 else x[lo] for lo, hi in ranges]
+        return list(torch.split(torch.stack(rows), counts)) if rows else []
+
+    monkeypatch.setattr(wordlevel, "_pool", cpu_pool)
+    g = golden("wordlevel")
+    text_emb, audio_emb, input_ids, offsets, text, bounds = wordlevel_case(g)
+    wt, wa, inv = wordlevel.get_word_level_embs(text_emb, text, input_ids, offsets, audio_emb=audio_emb, word_boundaries=bounds)
+    assert inv == list(g["invalid"]) and [len(x) for x in wt] == list(g["counts"])
+    assert np.allclose(torch.cat(wt).numpy(), g["word_text"], atol=1e-6) and np.allclose(torch.cat(wa).numpy(), g["word_audio"], atol=1e-6)
+    au, inv_a = wordlevel.get_audio_word_level_embs(audio_emb, bounds, list(inv))
+    assert inv_a == list(g["audio_only_invalid"]) and np.allclose(torch.cat(au).numpy(), g["audio_only"], atol=1e-6)
+    with pytest.raises(IndexError):  # an empty frame range fails like the reference's `[0]` on an empty tensor
+        wordlevel.get_audio_word_level_embs(torch.zeros(1, 10, 256), [[["a", 100, 104], ["b", 120, 125]]])
