@@ -18,16 +18,21 @@
 //     (16 KB per k-block), so every MMA reads A and B from smem and L2->smem
 //     traffic per MMA tile is halved with respect to streaming both operands;
 //   - warp 0: TMA producer, warp 1: tcgen05.mma issuer, warp 2: TMEM allocator,
-//     warps 4-7 / 8-11: two epilogue warpgroups (tcgen05.ld -> pooling -> global), one
-//     per TMEM accumulator buffer, so every SM sub-partition has two epilogue warps
-//     whose TMEM-load / shuffle latencies interleave;
+//     warps 4-7 / 8-11: two epilogue warpgroups (tcgen05.ld -> pooling -> global), so every
+//     SM sub-partition has two epilogue warps whose TMEM-load / shuffle latencies interleave.
+//     Fused modes: one warpgroup per TMEM accumulator buffer (every other tile each).
+//     Two-pass mode: both warpgroups drain every tile, one half of the columns each;
 //   - two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs
 //     of tiles i+1 and i+2; stationary-tile k-blocks are released one by one during the
 //     last row tile of a unit so the next column tile's load overlaps too;
 //   - work is split over clusters by "row-tile steps" inside L2-sized phases of
 //     R so that all CTAs stream the same slice of R at the same time;
 //   - ragged column tiles: the MMA N of a unit is roundup16(columns its clips occupy), so
-//     greedy whole-clip packing wastes no tensor time on the unused part of a 256-wide tile.
+//     greedy whole-clip packing wastes no tensor time on the unused part of a 256-wide tile;
+//   - two-pass mode (kRowOp == OP_NONE, chosen by the host for column sides made of many short
+//     clips or of clips longer than a tile): the kernel only pools along columns and stores the
+//     per-row values as M[column segment][row]; rowreduce_kernel (bottom of this file) combines
+//     the pieces of a clip, reduces over rows and applies the scales.
 #include <cstdio>
 
 #include "internal.h"
@@ -41,7 +46,7 @@ namespace {
 
 constexpr uint32_t kTileBytes = kTileRows * kBlockK * 2;  // 16384
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiGroups = 2;  // one epilogue warpgroup per TMEM accumulator buffer
+constexpr int kEpiGroups = 2;
 constexpr int kThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);  // 384
 
 template <int kOp>
@@ -801,19 +806,19 @@ int launch_rowreduce(jegal_ctx* ctx, const float* M, int64_t ldm, const int32_t*
                      const int32_t* cu_C, const int32_t* seg_C, int32_t n_cclips, int col_op, int row_op,
                      const float* rscale, const float* cscale, float* out, int64_t ld_r, int64_t ld_c,
                      cudaStream_t stream) {
-  const int32_t cgroups = (n_rclips + kRrClips - 1) / kRrClips;  // blocks per column clip
-  const int64_t blocks = static_cast<int64_t>(n_cclips) * cgroups;
+  const int32_t rblocks = (n_rclips + kRrClips - 1) / kRrClips;  // blocks per column clip
+  const int64_t blocks = static_cast<int64_t>(n_cclips) * rblocks;
   if (blocks <= 0) return JEGAL_OK;
   if (blocks > 0x7fffffff) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "rowreduce: more than 2^31 blocks");
   const unsigned g = static_cast<unsigned>(blocks);
   if (col_op == OP_MAX && row_op == OP_SUM) {
-    rowreduce_kernel<OP_MAX, OP_SUM><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, cgroups,
+    rowreduce_kernel<OP_MAX, OP_SUM><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, rblocks,
                                                             rscale, cscale, out, ld_r, ld_c);
   } else if (col_op == OP_MAX && row_op == OP_MAX) {
-    rowreduce_kernel<OP_MAX, OP_MAX><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, cgroups,
+    rowreduce_kernel<OP_MAX, OP_MAX><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, rblocks,
                                                             rscale, cscale, out, ld_r, ld_c);
   } else if (col_op == OP_SUM && row_op == OP_SUM) {
-    rowreduce_kernel<OP_SUM, OP_SUM><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, cgroups,
+    rowreduce_kernel<OP_SUM, OP_SUM><<<g, 256, 0, stream>>>(M, ldm, cu_R, n_rclips, cu_C, seg_C, n_cclips, rblocks,
                                                             rscale, cscale, out, ld_r, ld_c);
   } else {
     return set_err(ctx, JEGAL_ERR_ARG, "rowreduce: unsupported (col_op,row_op)");
