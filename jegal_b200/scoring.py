@@ -32,6 +32,7 @@ from . import ops
 from .ops import JegalError, Layout
 
 TEMP = 0.07  # evaluate_spotting.py:39, evaluate_asd.py:43, plot_heatmap.py:34
+GROUPED_MAX_WORDS = 64  # K3 / K4 keep a clip's words on <= 64 accumulator columns; wider clips take the K1 route
 ArrayLike = Union[np.ndarray, torch.Tensor, Sequence]
 
 _layout_cache: Dict[bytes, Layout] = {}
@@ -319,26 +320,68 @@ def spot_batch(gestures, contents, word_idx: Sequence[int], temp: float = TEMP, 
     dev = g.rows.device
     g16, _ = ops.prep(g.rows, g.layout, normalize=normalize, out_dtype=op_dtype)
     c16, _ = ops.prep(c.rows, c.layout, normalize=normalize, out_dtype=op_dtype)
-    wi = torch.as_tensor(np.asarray(word_idx, dtype=np.int32), device=dev)
-    lo = hi = None
+    word_idx = np.asarray(word_idx, dtype=np.int32)
+    lo_h = hi_h = None
     if windows is not None:
-        lo = torch.as_tensor(np.asarray(windows[0], dtype=np.int32), device=dev)
-        hi = torch.as_tensor(np.asarray(windows[1], dtype=np.int32), device=dev)
-    r = ops.spot(g16, g.layout, c16, c.layout, wi, tau=temp, want_heat=True, want_full=want_full,
-                 win_lo=lo, win_hi=hi, thresh=thresh)
-    cu_t = g.layout.cu_len
-    heat = r["heat"].cpu().numpy()
-    out = dict(
-        heat=[heat[cu_t[i]:cu_t[i + 1]] for i in range(g.n)],
-        pred_frame=r["pred_frame"].cpu().numpy(),
-        pred_score=r["pred_score"].cpu().numpy(),
-        correct=None if r["correct"] is None else r["correct"].cpu().numpy().astype(bool),
-    )
+        lo_h, hi_h = np.asarray(windows[0], dtype=np.int32), np.asarray(windows[1], dtype=np.int32)
+    lt, lw = g.layout.lengths, c.layout.lengths
+    cu_t, cu_w = g.layout.cu_len, c.layout.cu_len
+    wide = np.nonzero(lw > GROUPED_MAX_WORDS)[0]
+    n = g.n
+    heat_l: List[Optional[np.ndarray]] = [None] * n
+    full_l: List[Optional[np.ndarray]] = [None] * n
+    pred_frame = np.zeros(n, dtype=np.int32)
+    pred_score = np.zeros(n, dtype=np.float32)
+    correct = np.zeros(n, dtype=bool) if windows is not None else None
+
+    narrow = np.nonzero(lw <= GROUPED_MAX_WORDS)[0]
+    if len(narrow):
+        if len(wide) == 0:
+            gn16, cn16, gl_n, cl_n = g16, c16, g.layout, c.layout
+        else:  # K3 takes clip i of both layouts: gather the rows of the narrow clips (one device gather each)
+            keep = np.zeros(n, dtype=bool)
+            keep[narrow] = True
+            gn16 = g16[torch.from_numpy(np.repeat(keep, lt)).to(dev)]
+            cn16 = c16[torch.from_numpy(np.repeat(keep, lw)).to(dev)]
+            gl_n, cl_n = layout_for(lt[narrow]), layout_for(lw[narrow])
+        wi = torch.as_tensor(word_idx[narrow], device=dev)
+        lo = hi = None
+        if windows is not None:
+            lo, hi = torch.as_tensor(lo_h[narrow], device=dev), torch.as_tensor(hi_h[narrow], device=dev)
+        r = ops.spot(gn16, gl_n, cn16, cl_n, wi, tau=temp, want_heat=True, want_full=want_full,
+                     win_lo=lo, win_hi=hi, thresh=thresh)
+        cu_n = gl_n.cu_len
+        heat = r["heat"].cpu().numpy()
+        pred_frame[narrow] = r["pred_frame"].cpu().numpy()
+        pred_score[narrow] = r["pred_score"].cpu().numpy()
+        if correct is not None:
+            correct[narrow] = r["correct"].cpu().numpy().astype(bool)
+        if want_full:
+            full = r["full"].cpu().numpy()
+            off = r["full_off"].cpu().numpy()
+        for k_, i in enumerate(narrow):
+            heat_l[i] = heat[cu_n[k_]:cu_n[k_ + 1]]
+            if want_full:
+                full_l[i] = full[off[k_]:off[k_ + 1]].reshape(int(lw[i]), int(lt[i]))
+    for i in wide:
+        # more words than the grouped kernel's 64 columns (a long transcript): the same arithmetic from K1's
+        # plain-GEMM epilogue (frames x words cosines), the per-frame softmax over words and K2's first argmax
+        T, W = int(lt[i]), int(lw[i])
+        cos = ops.simpool_allpairs(g16[cu_t[i]:cu_t[i + 1]], layout_for(np.ones(T, dtype=np.int32)),
+                                   c16[cu_w[i]:cu_w[i + 1]], layout_for(np.ones(W, dtype=np.int32)), "mean_mean")
+        probs, _ = ops.group_softmax(cos.view(-1), T, W, tau=temp)  # [T, W]: softmax over words for each frame
+        row = probs[:, int(word_idx[i])].contiguous()
+        v, f = ops.topk(row.view(1, T), 1)
+        heat_l[i] = row.cpu().numpy()
+        pred_frame[i] = int(f[0, 0])
+        pred_score[i] = float(v[0, 0])
+        if correct is not None:
+            correct[i] = bool(lo_h[i] <= pred_frame[i] <= hi_h[i] and pred_score[i] >= thresh)
+        if want_full:
+            full_l[i] = probs.t().contiguous().cpu().numpy()
+    out = dict(heat=heat_l, pred_frame=pred_frame, pred_score=pred_score, correct=correct)
     if want_full:
-        full = r["full"].cpu().numpy()
-        off = r["full_off"].cpu().numpy()
-        lt, lw = g.layout.lengths, c.layout.lengths
-        out["full"] = [full[off[i]:off[i + 1]].reshape(int(lw[i]), int(lt[i])) for i in range(g.n)]
+        out["full"] = full_l
     return out
 
 
@@ -411,6 +454,39 @@ def get_similarity_cos(query_emb, data_emb, temp: float = TEMP) -> np.ndarray:
     return r["probs"].cpu().numpy()
 
 
+def _pair_scores(g16, gl: Layout, c16, cl: Layout, pg: torch.Tensor, pc: torch.Tensor, pool: str,
+                 gs: Optional[torch.Tensor], cs: Optional[torch.Tensor]) -> torch.Tensor:
+    """Pooled scores of the listed pairs: K4 for pairs whose content clip has <= 64 words, K1 on the
+    single pair (any clip lengths) for the rest."""
+    pc_h = pc.cpu().numpy()
+    wide = np.nonzero(cl.lengths[pc_h] > GROUPED_MAX_WORDS)[0] if pc_h.size else np.zeros(0, dtype=np.int64)
+    if len(wide) == 0:
+        return ops.simpool_pairs(g16, gl, c16, cl, pg, pc, pool, gscale=gs, cscale=cs)["scores"]
+    pg_h = pg.cpu().numpy()
+    scores = torch.empty((pg.numel(),), dtype=torch.float32, device=g16.device)
+    narrow = np.setdiff1d(np.arange(pg.numel()), wide)
+    if len(narrow):
+        # K4 validates the whole content layout: hand it the <= 64-word clips only (one device gather)
+        lw = cl.lengths
+        keep = lw <= GROUPED_MAX_WORDS
+        remap = np.cumsum(keep) - 1
+        cn16 = c16[torch.from_numpy(np.repeat(keep, lw)).to(g16.device)]
+        cs_n = None if cs is None else cs[torch.from_numpy(np.nonzero(keep)[0]).to(g16.device)].contiguous()
+        sel = torch.from_numpy(narrow).to(g16.device)
+        pc_n = torch.from_numpy(remap[pc_h[narrow]].astype(np.int32)).to(g16.device)
+        scores[sel] = ops.simpool_pairs(g16, gl, cn16, layout_for(lw[keep]), pg[sel].contiguous(), pc_n, pool,
+                                        gscale=gs, cscale=cs_n)["scores"]
+    cu_t, cu_w = gl.cu_len, cl.cu_len
+    for p in wide:
+        gi, ci = int(pg_h[p]), int(pc_h[p])
+        one = ops.simpool_allpairs(g16[cu_t[gi]:cu_t[gi + 1]], layout_for([cu_t[gi + 1] - cu_t[gi]]),
+                                   c16[cu_w[ci]:cu_w[ci + 1]], layout_for([cu_w[ci + 1] - cu_w[ci]]), pool,
+                                   gscale=None if gs is None else gs[gi:gi + 1],
+                                   cscale=None if cs is None else cs[ci:ci + 1])
+        scores[p] = one[0, 0]
+    return scores
+
+
 def asd_batch(contents, gesture_tracks, pair_gest: Sequence[int], pair_cont: Sequence[int], tracks: int,
               prefixes: Sequence[int] = (2, 4, 6), temp: float = TEMP, mode: str = "reference",
               op_dtype: torch.dtype = torch.bfloat16) -> dict:
@@ -435,13 +511,13 @@ def asd_batch(contents, gesture_tracks, pair_gest: Sequence[int], pair_cont: Seq
         g16, gs = ops.prep(g.rows, g.layout, out_dtype=op_dtype)
         c16, cs = ops.prep(c.rows, c.layout, out_dtype=op_dtype)
         pool = mode
-    r = ops.simpool_pairs(g16, g.layout, c16, c.layout, pg, pc, pool, gscale=gs, cscale=cs)
+    scores = _pair_scores(g16, g.layout, c16, c.layout, pg, pc, pool, gs, cs)
     n_groups = pg.numel() // tracks
     pred, acc = {}, {}
     for P in prefixes:
         if P > tracks:
             continue
-        _, am = ops.group_softmax(r["scores"], n_groups, P, stride=tracks, tau=temp, want_probs=False)
+        _, am = ops.group_softmax(scores, n_groups, P, stride=tracks, tau=temp, want_probs=False)
         pred[P] = am.cpu().numpy()
         acc[P] = float((pred[P] == 0).mean()) if n_groups else float("nan")
-    return dict(scores=r["scores"].cpu().numpy().reshape(n_groups, tracks), pred=pred, acc=acc)
+    return dict(scores=scores.cpu().numpy().reshape(n_groups, tracks), pred=pred, acc=acc)

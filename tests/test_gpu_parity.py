@@ -324,11 +324,16 @@ def test_spotting_long_and_edge_clips(dev):
         assert abs(r["pred_score"][i] - row.max()) < PROB_TOL
 
 
-def test_spotting_rejects_too_many_words(dev):
-    from jegal_b200 import scoring
+def test_k3_rejects_too_many_words_at_the_op_level(dev):
+    """The grouped kernel itself keeps its 64-column limit (the host mirror routes wider clips elsewhere)."""
+    from jegal_b200 import ops
     from jegal_b200._lib import JegalError
+    g, c = rand_clips(1, 30, 30, 46), rand_clips(1, 65, 65, 47)
+    gl, cl = ops.Layout.from_lengths([30]), ops.Layout.from_lengths([65])
+    g16, _ = ops.prep(torch.from_numpy(g[0]).to(dev), gl)
+    c16, _ = ops.prep(torch.from_numpy(c[0]).to(dev), cl)
     with pytest.raises(JegalError, match="words"):
-        scoring.spot_batch(rand_clips(1, 30, 30, 46), rand_clips(1, 65, 65, 47), [0])
+        ops.spot(g16, gl, c16, cl, torch.zeros(1, dtype=torch.int32, device=dev))
 
 
 # ----------------------------------------------------------------------------- K4
@@ -594,3 +599,52 @@ def test_embedding_sink_device_path_equals_pkl_round_trip(dev, tmp_path):
         from_pkl = scoring.score_allpairs(d["gesture"], d["content"], mode)
         ref = oracle.simpool_allpairs(d["gesture"], d["content"], mode)
         assert np.abs(from_dev - ref).max() < TOL and np.abs(from_pkl - ref).max() < TOL
+
+
+# ----------------------------------------------------------------------------- clips with more than 64 words
+def test_spotting_clips_with_more_than_64_words(dev):
+    """Long transcripts (W > 64 words) leave the grouped kernel's column budget: the host mirror routes them
+    through K1's plain-GEMM epilogue + the per-frame softmax + K2's argmax, mixed freely with ordinary clips."""
+    from jegal_b200 import scoring
+    rng = np.random.default_rng(41)
+    shapes = [(56, 8), (300, 100), (40, 12), (200, 70), (90, 65)]
+    gest = [rand_clips(1, T, T, 50 + i)[0] for i, (T, W) in enumerate(shapes)]
+    cont = [rand_clips(1, W, W, 60 + i)[0] for i, (T, W) in enumerate(shapes)]
+    # correlate a few frames with their target word so that decisions are not all trivial
+    tw = [int(rng.integers(0, W)) for (T, W) in shapes]
+    for i, (T, W) in enumerate(shapes):
+        g = gest[i].astype(np.float32)
+        g[T // 2] = cont[i][tw[i]].astype(np.float32)
+        gest[i] = g.astype(np.float16)
+    lo = np.zeros(len(shapes), dtype=np.int32)
+    hi = np.array([T for T, _ in shapes], dtype=np.int32)
+    r = scoring.spot_batch(gest, cont, tw, windows=(lo, hi), want_full=True)
+    for i, (T, W) in enumerate(shapes):
+        ref = oracle.get_attn_matrix(gest[i], cont[i])
+        assert r["full"][i].shape == (W, T) and np.abs(r["full"][i] - ref).max() < PROB_TOL
+        assert np.abs(r["heat"][i] - ref[tw[i]]).max() < PROB_TOL
+        pred, score, ok = oracle.spot_decision(ref, tw[i], 0, T, frame_thresh=0)
+        assert r["pred_frame"][i] == pred == T // 2 and abs(r["pred_score"][i] - score) < PROB_TOL
+        assert bool(r["correct"][i]) == ok
+    a, words = scoring.get_attn_matrix(gest[1], cont[1], [[f"w{k}", k, k] for k in range(100)])
+    assert a.shape == (100, 300) and len(words) == 100
+    assert np.abs(a - oracle.get_attn_matrix(gest[1], cont[1], normalize=False)).max() < PROB_TOL
+
+
+@pytest.mark.parametrize("mode", ["reference", "max_t_mean_w", "max_max"])
+def test_asd_with_a_content_track_of_more_than_64_words(dev, mode):
+    from jegal_b200 import scoring
+    cont = rand_clips(2, 70, 95, 71) + rand_clips(3, 5, 17, 72)          # two wide content tracks
+    gest = rand_clips(5 * 4, 39, 191, 73)
+    pair_gest = np.arange(20, dtype=np.int32)
+    pair_cont = np.repeat(np.arange(5, dtype=np.int32), 4)
+    r = scoring.asd_batch(cont, gest, pair_gest, pair_cont, 4, prefixes=(4,), mode=mode)
+    for p in range(20):
+        g, c = gest[pair_gest[p]], cont[pair_cont[p]]
+        if mode == "reference":
+            q = oracle.asd_mean_emb(c)
+            d = oracle.asd_mean_emb(g)
+            want = float(torch.nn.functional.cosine_similarity(q, d, dim=1, eps=1e-8)[0])
+        else:
+            want = float(oracle.simpool_allpairs([g], [c], mode)[0, 0])
+        assert abs(r["scores"].reshape(-1)[p] - want) < TOL, (mode, p)
