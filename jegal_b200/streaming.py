@@ -17,6 +17,27 @@ from . import ops
 from .ops import JegalError
 
 
+def chunk_schedule(n_clips: int, chunk_clips: int, ramp: bool = True):
+    """Clip counts of the successive gallery chunks.  Scoring cannot start before the first chunk has arrived
+    and cannot finish before the last chunk's copy + its scoring, so with ``ramp`` the chunks grow geometrically
+    at the start (chunk/8, /8, /4, /2), stay at full size in the middle and shrink again at the end
+    (/2, /4, /8, /8): the start-up latency is the copy of 1/8 chunk, and when the copies are the bottleneck
+    (several GPUs pulling from one host) the tail after the last copy is the scoring of 1/8 chunk."""
+    n, c = int(n_clips), max(1, int(chunk_clips))
+    if n <= 0:
+        return []
+    if not ramp or c < 64:
+        return [c] * (n // c) + ([n % c] if n % c else [])
+    while n < 2 * c and c >= 128:
+        c //= 2
+    if n < 2 * c:
+        return [n]
+    up = [c // 8, c // 8, c // 4, c // 2]
+    down = up[::-1]
+    mid = n - 2 * c
+    return up + [c] * (mid // c) + ([mid % c] if mid % c else []) + down
+
+
 class StreamedGallery:
     """Pinned host gallery (packed fp16/fp32 rows + per-clip lengths) cut into clip-aligned chunks."""
 
@@ -29,15 +50,10 @@ class StreamedGallery:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.idx_base = idx_base
         cu = np.concatenate([[0], np.cumsum(self.lengths)])
-        # Scoring cannot start before the first chunk has arrived, so the first chunks are small and grow
-        # geometrically (chunk_clips / 8, / 8, / 4, / 2, then full size): the start-up latency is the copy of
-        # 1/8 chunk instead of a whole one, and the small launches at the start cost little.
         self.chunks = []
-        sizes = [max(1, chunk_clips // d) for d in (8, 8, 4, 2)] if ramp and chunk_clips >= 64 else []
         lo = 0
-        while lo < len(self.lengths):
-            size = sizes.pop(0) if sizes else chunk_clips
-            hi = min(lo + size, len(self.lengths))
+        for size in chunk_schedule(len(self.lengths), chunk_clips, ramp):
+            hi = lo + size
             self.chunks.append((lo, hi, int(cu[lo]), int(cu[hi]), ops.Layout.from_lengths(self.lengths[lo:hi])))
             lo = hi
         max_rows = max((c[3] - c[2] for c in self.chunks), default=0)

@@ -286,3 +286,13 @@ def test_wordlevel_range_logic_against_reference_golden(golden, monkeypatch):
     assert inv_a == list(g["audio_only_invalid"]) and np.allclose(torch.cat(au).numpy(), g["audio_only"], atol=1e-6)
     with pytest.raises(IndexError):  # an empty frame range fails like the reference's `[0]` on an empty tensor
         wordlevel.get_audio_word_level_embs(torch.zeros(1, 10, 256), [[["a", 100, 104], ["b", 120, 125]]])
+
+
+def test_streaming_chunk_schedule():
+    from jegal_b200.streaming import chunk_schedule
+    for n, c in [(8192, 2048), (65536, 8192), (301, 64), (100, 64), (5, 64), (4096, 2048), (10000, 2048), (0, 64), (130, 64)]:
+        sch = chunk_schedule(n, c)
+        assert sum(sch) == n and all(x > 0 for x in sch) and max(sch, default=0) <= max(c, n if n < 128 else c)
+        if len(sch) >= 8:  # ramps up at the start, down at the end
+            assert sch[0] <= sch[2] <= sch[3] and sch[-1] <= sch[-3] <= sch[-4]
+    assert chunk_schedule(300, 64, ramp=False) == [64, 64, 64, 64, 44]
