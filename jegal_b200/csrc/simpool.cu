@@ -734,38 +734,43 @@ rowreduce_kernel(const float* __restrict__ M, int64_t ldm, const int32_t* __rest
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = op_ident<kRowOp>();
   if (np == 1) {
-    // One 16-byte load per lane covers 128 rows of a clip per step; 8 clips in lock step = 4 KB in flight per
-    // warp and round trip to DRAM (with 4-byte loads the kernel sat at 2.6 TB/s: too few bytes in flight).
-    // Loads start at the 16-byte boundary below the clip; elements outside [begin, end) are masked by select.
-    const float4* ptr[8];
-    int32_t lo[8], hi[8];  // this lane's float4 holds rows lo..hi-1 (relative to its first element) of clip j
+    // A clip's rows [r0, r1) are split into an aligned interior [a, b) read with unmasked 16-byte loads (one
+    // per lane covers 128 rows per step; 8 clips in lock step = 4 KB in flight per warp and round trip) and
+    // at most 3 + 3 edge rows read by lanes 0-2 / 4-6 with one scalar load each.  (Masking every element of
+    // every 16-byte load cost 24 instructions per load and kept the kernel half issue-bound at 2.6 TB/s.)
+    const float4* p4[8];
+    int32_t n4[8];  // 16-byte loads this lane still has to do for clip j
+    float edge[8];
+    int32_t longest4 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int32_t a = bnd[j] & ~3;
-      ptr[j] = reinterpret_cast<const float4*>(src + a) + lane;
-      lo[j] = bnd[j] - a - 4 * lane;
-      hi[j] = bnd[j + 1] - a - 4 * lane;
+      const int32_t r0 = bnd[j], r1 = bnd[j + 1];
+      const int32_t a = min((r0 + 3) & ~3, r1);  // head rows [r0, a)
+      const int32_t b = max(r1 & ~3, a);         // tail rows [b, r1)
+      const int32_t idx = lane < 4 ? r0 + lane : b + lane - 4;
+      const bool ok = lane < 4 ? idx < a : (lane < 8 && idx < r1);
+      edge[j] = op_ident<kRowOp>();
+      if (ok) edge[j] = __ldcs(src + idx);
+      p4[j] = reinterpret_cast<const float4*>(src + a) + lane;
+      n4[j] = ((b - a) >> 2) - lane;
+      longest4 = max(longest4, (b - a) >> 2);
     }
-    for (int32_t k = 0; k < longest + 3; k += 128) {
+    for (int32_t k = 0; k < longest4; k += 32) {
       float4 x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (hi[j] > 0) x[j] = __ldcs(ptr[j]);
+        const float id = op_ident<kRowOp>();
+        x[j] = make_float4(id, id, id, id);
+        if (n4[j] > 0) x[j] = __ldcs(p4[j]);
+        p4[j] += 32;
+        n4[j] -= 32;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float id = op_ident<kRowOp>();
-        const float e0 = (lo[j] <= 0 && hi[j] > 0) ? x[j].x : id;
-        const float e1 = (lo[j] <= 1 && hi[j] > 1) ? x[j].y : id;
-        const float e2 = (lo[j] <= 2 && hi[j] > 2) ? x[j].z : id;
-        const float e3 = (lo[j] <= 3 && hi[j] > 3) ? x[j].w : id;
-        v[j] = op_apply<kRowOp>(v[j], op_apply<kRowOp>(op_apply<kRowOp>(e0, e1), op_apply<kRowOp>(e2, e3)));
-        ptr[j] += 32;
-        lo[j] -= 128;
-        hi[j] -= 128;
-      }
+      for (int j = 0; j < 8; ++j)
+        v[j] = op_apply<kRowOp>(v[j], op_apply<kRowOp>(op_apply<kRowOp>(x[j].x, x[j].y), op_apply<kRowOp>(x[j].z, x[j].w)));
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = op_apply<kRowOp>(v[j], edge[j]);
   } else {
     for (int32_t k = lane; k < longest; k += 32) {
 #pragma unroll
