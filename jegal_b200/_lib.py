@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library for sm_100a with nvcc (no GPU needed)."""
     if force:
         subprocess.run(["make", "-C", CSRC_DIR, "clean"], check=True, capture_output=not verbose)
-    r = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout)
         print(r.stderr)
