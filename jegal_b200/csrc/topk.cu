@@ -6,6 +6,7 @@
 // Ordering rule everywhere: descending score, ties towards the LOWER index, so a
 // gallery sharded over several GPUs merges to exactly the single-GPU list.
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -250,7 +251,9 @@ int launch_topk(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g, i
   if (n_q <= 0) return JEGAL_OK;
   // rows are only sliced when there are too few of them to fill the GPU (every slice pays the start-up
   // phase of an empty list again); at least 16 K floats per block
-  const int64_t capacity = static_cast<int64_t>(ctx->sm_count) * 8;
+  const char* cap_env = std::getenv("JEGAL_TOPK_BLOCKS_PER_SM");  // tuning knob; default 8
+  const int64_t per_sm = cap_env && *cap_env ? std::max(1, std::atoi(cap_env)) : 8;
+  const int64_t capacity = static_cast<int64_t>(ctx->sm_count) * per_sm;
   int64_t slices = capacity / n_q;
   slices = std::min<int64_t>(slices, std::max<int64_t>(1, n_g / 16384));
   slices = std::max<int64_t>(1, std::min<int64_t>(slices, 64));
