@@ -104,8 +104,6 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
     dev = gallery.dev
     main = torch.cuda.current_stream(dev)
     nq = q_layout.n_clips
-    if not gallery.chunks:
-        return (torch.full((nq, k), float("-inf"), device=dev), torch.full((nq, k), -1, dtype=torch.int32, device=dev))
     import torch.distributed as dist
 
     bcast = bcast_src is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -128,6 +126,11 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
                     ready[p] = torch.cuda.Event()
                     ready[p].record(gallery.q_stream)
         q_dev.record_stream(gallery.q_stream)
+    if not gallery.chunks:  # an empty shard still took part in the broadcast above (it is a collective)
+        for r in ready:
+            if r is not None and not isinstance(r, torch.cuda.Event):
+                r.wait()
+        return (torch.full((nq, k), float("-inf"), device=dev), torch.full((nq, k), -1, dtype=torch.int32, device=dev))
     q16 = torch.empty((q_layout.rows, 512), dtype=torch.bfloat16, device=dev)
     vals = torch.empty((len(gallery.chunks), nq, k), dtype=torch.float32, device=dev)
     idxs = torch.empty((len(gallery.chunks), nq, k), dtype=torch.int32, device=dev)
