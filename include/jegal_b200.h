@@ -93,6 +93,23 @@ int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, 
                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
                float* inv_meannorm_dev, void* mean_rows_dev, void* stream);
 
+/* K0 without the row output: one read-only pass that yields, per clip, the unit-norm mean row
+ * (mean over the clip's INPUT rows, divided by max(||mean||, mean_eps)) in `out_dtype` (JEGAL_F32, JEGAL_F16 or
+ * JEGAL_BF16; nullable) and/or 1 / max(||mean||, mean_eps) (nullable).  This is load_feats' temporal mean of
+ * evaluate_retrieval.py:30-31 / evaluate_asd.py:31-36 (numpy's fp16 result rounding is mirrored for fp16
+ * inputs) followed by the norm of F.normalize / CosineSimilarity; bytes: rows x 512 x b_in read, n_clips rows written. */
+int jegal_clip_means(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype, float mean_eps,
+                     int out_dtype, void* mean_rows_dev, float* inv_meannorm_dev, void* stream);
+
+/* Cosine (normalize = 1) or dot product (0) of LISTED pairs of 512-wide rows, one warp per pair:
+ *   scores[p] = a[pair_a[p]] . b[pair_b[p]] / (max(||a||, eps) max(||b||, eps))
+ * — nn.CosineSimilarity(dim=1, eps=1e-8) of evaluate_asd.py:45-47 on clip-level embeddings (the outputs of
+ * jegal_clip_means, or get_similarity_cos' (1, 512) / (P, 512) arguments).  Both matrices are [n, 512] in
+ * `dtype` (JEGAL_F32 / F16 / BF16); pair_a / pair_b nullable (=> p). */
+int jegal_pair_cosine(jegal_ctx* ctx, const void* a_rows_dev, int64_t n_a, const void* b_rows_dev, int64_t n_b,
+                      int dtype, const int32_t* pair_a_dev, const int32_t* pair_b_dev, int32_t n_pairs,
+                      int normalize, float eps, float* scores_dev, void* stream);
+
 /* K1 — all-pairs fused similarity + pooling (tcgen05 / TMEM / TMA).
  * scores[g * ld_g + c * ld_c] = gscale[g] * cscale[c] * pool_{t,w}(G_g C_c^T).
  * Generalises get_similarity_matrix (evaluation/evaluate_retrieval.py:38-48) from
@@ -150,6 +167,12 @@ int jegal_rank_of_positive(jegal_ctx* ctx, const float* scores_dev, int32_t n_q,
 
 /* K3 — word spotting (evaluation/evaluate_spotting.py:39-90, utils/plot_heatmap.py:34-59).
  * For clip i: A = softmax_w((G_i C_i^T) / tau) (softmax over words per frame).
+ *   normalize_rows    1: gest_rows_dev / cont_rows_dev are the rows AS STORED in the .pkl files (op_dtype =
+ *                     JEGAL_F16, or JEGAL_BF16) and the L2 normalisation of evaluate_spotting.py:49-50 is fused
+ *                     into the load: the kernel derives 1 / max(||row||, row_eps) of every frame and word from
+ *                     the staged operand bytes and scales the accumulator — no normalised copy exists in HBM.
+ *                     0: the rows are used as they are (outputs of jegal_prep, or plot_heatmap.py:51-57 which
+ *                     does not re-normalise).
  *   word_idx_dev[i]   the target word's row of A^T
  *   heat_dev          (nullable) [rows of gest_layout] fp32: A[:, word_idx] for every frame
  *   full_heat_dev     (nullable) [sum_i T_i * W_i] fp32: the whole (W_i x T_i) matrix of clip i,
@@ -160,21 +183,22 @@ int jegal_rank_of_positive(jegal_ctx* ctx, const float* scores_dev, int32_t n_q,
  */
 int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
                const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
-               const int32_t* word_idx_dev, float tau, float* heat_dev, float* full_heat_dev,
+               int normalize_rows, float row_eps, const int32_t* word_idx_dev, float tau, float* heat_dev, float* full_heat_dev,
                const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
                const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh,
                uint8_t* correct_dev, void* stream);
 
 /* K4 — grouped scoring (evaluation/evaluate_asd.py:43-51,94-100): n_pairs listed
  * (gesture clip, content clip) pairs in groups of `group_size` consecutive pairs.
+ *   normalize_rows / row_eps: as in jegal_spot (row normalisation fused into the load)
  *   scores_dev[p]  pooled score of pair p (x gscale x cscale as in K1)
  *   probs_dev      (nullable) softmax(scores / tau) within each group
  *   argmax_dev     (nullable) [n_pairs / group_size] first index of the group maximum
  */
 int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
                         const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
-                        int pool_mode, const float* gscale_dev, const float* cscale_dev,
-                        const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
+                        int normalize_rows, float row_eps, int pool_mode, const float* gscale_dev,
+                        const float* cscale_dev, const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
                         int32_t group_size, float tau, float* scores_dev, float* probs_dev,
                         int32_t* argmax_dev, void* stream);
 

@@ -41,6 +41,8 @@ SYMBOLS = [
     "jegal_exchange_destroy",
     "jegal_topk_exchange",
     "jegal_segment_mean",
+    "jegal_clip_means",
+    "jegal_pair_cosine",
 ]
 
 F32, F16, BF16 = 0, 1, 2
@@ -104,9 +106,9 @@ def load() -> C.CDLL:
     lib.jegal_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.jegal_rank_of_positive.argtypes = [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp]
     if hasattr(lib, "jegal_spot"):
-        lib.jegal_spot.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, f32, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp]
+        lib.jegal_spot.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, f32, vp, f32, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp]
     if hasattr(lib, "jegal_simpool_pairs"):
-        lib.jegal_simpool_pairs.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]
+        lib.jegal_simpool_pairs.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, f32, C.c_int, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]
     if hasattr(lib, "jegal_group_softmax"):
         lib.jegal_group_softmax.argtypes = [vp, vp, i32, i32, i64, f32, vp, vp, vp]
     if hasattr(lib, "jegal_topk_exchange"):
@@ -118,6 +120,10 @@ def load() -> C.CDLL:
         lib.jegal_topk_exchange.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
     if hasattr(lib, "jegal_segment_mean"):
         lib.jegal_segment_mean.argtypes = [vp, vp, C.c_int, i64, i32, vp, vp, i32, vp, C.c_int, i64, i32, vp]
+    if hasattr(lib, "jegal_clip_means"):
+        lib.jegal_clip_means.argtypes = [vp, vp, vp, C.c_int, f32, C.c_int, vp, vp, vp]
+    if hasattr(lib, "jegal_pair_cosine"):
+        lib.jegal_pair_cosine.argtypes = [vp, vp, i64, vp, i64, C.c_int, vp, vp, i32, C.c_int, f32, vp, vp]
     if hasattr(lib, "jegal_plan_column_tiles"):
         lib.jegal_plan_column_tiles.argtypes = [C.POINTER(i32), i32, i32, i32, vp, i32, C.POINTER(i32)]
     for name in SYMBOLS:

@@ -310,6 +310,35 @@ int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, 
                      out_rows_dev, inv_meannorm_dev, mean_rows_dev, static_cast<cudaStream_t>(stream));
 }
 
+int jegal_clip_means(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype, float mean_eps,
+                     int out_dtype, void* mean_rows_dev, float* inv_meannorm_dev, void* stream) {
+  if (!ctx || !layout) return set_err(ctx, JEGAL_ERR_ARG, "clip_means: null argument");
+  if (layout->n_clips == 0) return JEGAL_OK;
+  if (!emb_dev || (!mean_rows_dev && !inv_meannorm_dev)) return set_err(ctx, JEGAL_ERR_ARG, "clip_means: null argument");
+  if ((reinterpret_cast<uintptr_t>(emb_dev) | reinterpret_cast<uintptr_t>(mean_rows_dev)) & 15u)
+    return set_err(ctx, JEGAL_ERR_ARG, "clip_means: buffers must be 16-byte aligned");
+  if (out_dtype != JEGAL_F32 && out_dtype != JEGAL_F16 && out_dtype != JEGAL_BF16)
+    return set_err(ctx, JEGAL_ERR_ARG, "clip_means: bad out_dtype");
+  return launch_prep(ctx, layout, emb_dev, in_dtype, 0, 1e-12f, mean_eps, out_dtype, nullptr, inv_meannorm_dev,
+                     mean_rows_dev, static_cast<cudaStream_t>(stream));
+}
+
+int jegal_pair_cosine(jegal_ctx* ctx, const void* a_rows_dev, int64_t n_a, const void* b_rows_dev, int64_t n_b,
+                      int dtype, const int32_t* pair_a_dev, const int32_t* pair_b_dev, int32_t n_pairs,
+                      int normalize, float eps, float* scores_dev, void* stream) {
+  if (!ctx) return JEGAL_ERR_ARG;
+  if (n_pairs < 0 || n_a < 0 || n_b < 0) return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: negative size");
+  if (n_pairs == 0) return JEGAL_OK;
+  if (!a_rows_dev || !b_rows_dev || !scores_dev) return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: null argument");
+  if ((!pair_a_dev && n_pairs > n_a) || (!pair_b_dev && n_pairs > n_b))
+    return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: n_pairs exceeds the rows of an unlisted side");
+  if ((reinterpret_cast<uintptr_t>(a_rows_dev) | reinterpret_cast<uintptr_t>(b_rows_dev)) & 15u)
+    return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: rows must be 16-byte aligned");
+  if (normalize && !(eps > 0.f)) return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: eps must be > 0");
+  return launch_pair_cosine(ctx, a_rows_dev, b_rows_dev, dtype, pair_a_dev, pair_b_dev, n_pairs, normalize, eps,
+                            scores_dev, static_cast<cudaStream_t>(stream));
+}
+
 int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
                            const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
                            int pool_mode, const float* gscale_dev, const float* cscale_dev,

@@ -16,8 +16,27 @@
 //   warp 1  tcgen05.mma issuer: M = 128, N = roundup16(W), 32 MMAs per row tile
 //   warp 2  TMEM allocator (4 accumulator buffers of 64 columns)
 //   warps 4-7 epilogue: tcgen05.ld -> softmax / pooling -> coalesced stores
+//   warps 8-15 (kFuse only) row norms: the L2 normalisation of the reference
+//           (F.normalize at evaluate_spotting.py:49-50, CosineSimilarity's clamped norms at
+//           evaluate_asd.py:45-47) is FUSED INTO THE LOAD: the operands are the rows exactly as
+//           the .pkl stores them (fp16, or bf16), TMA stages them once, the tensor core contracts
+//           the raw rows, and these warps re-read the staged k-blocks from shared memory (a row's
+//           128 bytes stay inside its own swizzled line, so a sum of squares needs no
+//           un-swizzling): norm warp k owns k-block k of every row tile, adds its partial
+//           sum(x^2) of every frame / word into a per-tile table, and the epilogue scales lane
+//           (frame) and column (word) by rsqrt(max(sum, eps^2)) = 1 / max(||row||, eps).
+//           No normalised copy of the operands ever exists in HBM: bytes per clip are the
+//           (T + W) x 1 KB of the stored rows, read once.
+//           (One warp per k-block, not one warp per row range of every k-block: a warp walks the
+//           stage sequence serially -- wait, load, arrive -- at ~700 cycles per iteration whatever
+//           the payload, measured with JEGAL_GROUPED_TRACE; eight warps take one stage in eight.)
 //
 // Items are dealt round-robin to a persistent grid of one CTA per SM.
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -28,6 +47,9 @@ using namespace ptx;
 namespace {
 
 constexpr int kGThreads = 256;
+constexpr int kGThreadsFuse = 512;                // + 8 row-norm warps, one per k-block
+constexpr int kNormWarp0 = 8;
+constexpr int kNormRows = 192;                    // per accumulator buffer: 128 frame slots + 64 word slots
 constexpr int kGStages = 32;                     // barrier slots; smem is a BYTE ring (see RingAlloc)
 constexpr int kNMax = 64;                        // words per clip on the N side
 constexpr uint32_t kGRingBytes = 216 * 1024;     // operand ring: a stage takes only the bytes it loads
@@ -57,6 +79,8 @@ struct GroupedParams {
   float thresh;
   uint8_t* correct;
   // pooling
+  float row_eps;          // kFuse: 1 / max(||row||, row_eps)
+  unsigned long long* trace;  // nullable debug buffer: 16 cycle counters per CTA (JEGAL_GROUPED_TRACE=1)
   int32_t pool_mode;
   const float* gscale;
   const float* cscale;
@@ -108,10 +132,74 @@ struct RingAlloc {
   }
 };
 
+// cycle accounting, compiled in with -DJEGAL_GTRACE (make EXTRA=-DJEGAL_GTRACE) and switched on with
+// JEGAL_GROUPED_TRACE=1: tr[slot] += cycles spent in `stmt`.  Off by default: the duplicated wait sites cost
+// instruction-cache space the kernel does not have (ncu: stall_no_inst was the top stall reason).
+#ifdef JEGAL_GTRACE
+#define JEGAL_GTRACED(slot, stmt)                                        \
+  do {                                                                   \
+    if (JEGAL_GTRACE_ON(p)) {                                                       \
+      const long long t0__ = clock64();                                  \
+      stmt;                                                              \
+      tr[slot] += static_cast<unsigned long long>(clock64() - t0__);     \
+    } else {                                                             \
+      stmt;                                                              \
+    }                                                                    \
+  } while (0)
+#define JEGAL_GTRACE_ON(p) ((p).trace != nullptr)
+#else
+#define JEGAL_GTRACED(slot, stmt) do { stmt; } while (0)
+#define JEGAL_GTRACE_ON(p) false
+#endif
+
 __device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int kEpi>
-__global__ void __launch_bounds__(kGThreads, 1)
+// sum of squares of the 8 16-bit values of one 16-byte chunk, accumulated in fp32.
+// kImpl 0: widen to fp32 (HADD2.F32 / a shift for bf16) + FFMA; kImpl 1: the mixed-precision fma of sm_100
+// (FHFMA takes the half of a packed register directly: half the instructions -- measured A/B)
+template <bool kBf16, int kImpl>
+__device__ __forceinline__ float sumsq8(uint4 r, float acc) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  if constexpr (kImpl == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned short lo = static_cast<unsigned short>(w[i] & 0xffffu), hi = static_cast<unsigned short>(w[i] >> 16);
+      if constexpr (kBf16) {
+        asm("fma.rn.f32.bf16 %0, %1, %1, %0;" : "+f"(acc) : "h"(lo));
+        asm("fma.rn.f32.bf16 %0, %1, %1, %0;" : "+f"(acc) : "h"(hi));
+      } else {
+        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(acc) : "h"(lo));
+        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(acc) : "h"(hi));
+      }
+    }
+    return acc;
+  } else {
+    float a0 = acc, a1 = 0.f;  // two chains per chunk
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x, y;
+      if constexpr (kBf16) {
+        x = __uint_as_float(w[i] << 16);
+        y = __uint_as_float(w[i] & 0xffff0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        x = f.x;
+        y = f.y;
+      }
+      a0 = fmaf(x, x, a0);
+      a1 = fmaf(y, y, a1);
+    }
+    return a0 + a1;
+  }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+template <int kEpi, int kFuse>
+__global__ void __launch_bounds__(kFuse ? kGThreadsFuse : kGThreads, 1)
 grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -129,6 +217,13 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   float* epi_f0 = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
   int32_t* epi_i0 = reinterpret_cast<int32_t*>(epi_f0 + 2 * kScratchF);
   volatile uint32_t* need_smem = reinterpret_cast<volatile uint32_t*>(epi_i0 + 8);  // [kGStages], producer-private
+  // kFuse: sum of squares of the rows of the tile in accumulator buffer b: [b][0..127] frames, [b][128..191] words;
+  // inv_w: per epilogue warp, the 64 inverse word norms of the tile it is draining
+  float* ssq = reinterpret_cast<float*>(const_cast<uint32_t*>(need_smem) + kGStages);
+  float* inv_w = ssq + kNumAcc * kNormRows;
+  const uint32_t n_full0 = smem_u32(inv_w + 4 * kNMax);
+  auto n_full = [&](int b) { return n_full0 + 8u * b; };              // all 8 partial sums of a tile are in
+  auto z_full = [&](int b) { return n_full0 + 8u * (kNumAcc + b); };  // k-block 0's sums are stored (the others add)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,11 +232,15 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kGStages; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(empty(s), kFuse ? 2 : 1);  // the MMAs' commit (+ the row-norm warp that owns the k-block)
     }
     for (int b = 0; b < kNumAcc; ++b) {
       mbar_init(t_full(b), 1);
       mbar_init(t_empty(b), 4);
+      if constexpr (kFuse != 0) {
+        mbar_init(n_full(b), kNumKBlocks);
+        mbar_init(z_full(b), 1);
+      }
     }
     fence_mbar_init();
   }
@@ -157,6 +256,10 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
       // stage n uses barrier slot n % kGStages; `inflight` = ring bytes of stages not yet released.
       // The bookkeeping of released bytes goes through a small smem array (need_smem).
       uint32_t slot = 0, old_slot = 0, old_phase = 0, n_out = 0, inflight = 0;
+      unsigned long long tr[4] = {0, 0, 0, 0};
+      const long long t_begin = JEGAL_GTRACE_ON(p) ? clock64() : 0;
+      (void)tr;
+      (void)t_begin;
       RingAlloc ring;
       Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
       for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
@@ -177,7 +280,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
             const uint32_t off = base + ring.place(bytes, need);
             // free ring space / a barrier slot by retiring the oldest stages (the MMAs release in order)
             while (inflight + need > kGRingBytes || n_out >= kGStages) {
-              mbar_wait(empty(old_slot), old_phase);
+              JEGAL_GTRACED(0, mbar_wait_lean(empty(old_slot), old_phase));
               inflight -= need_smem[old_slot];
               --n_out;
               if (++old_slot == kGStages) {
@@ -196,10 +299,19 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           }
         }
       }
+      if (JEGAL_GTRACE_ON(p)) {
+        unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
+        g[0] = tr[0];
+        g[1] = static_cast<unsigned long long>(clock64() - t_begin);
+      }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       uint32_t slot = 0, phase = 0, tile = 0;
+      unsigned long long tr[4] = {0, 0, 0, 0};
+      const long long t_begin = JEGAL_GTRACE_ON(p) ? clock64() : 0;
+      (void)tr;
+      (void)t_begin;
       RingAlloc ring;
       Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
       for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
@@ -211,14 +323,14 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           const uint32_t bytes_g = ((rows + kBoxG - 1) / kBoxG) * (kBoxG * 128);
           const uint32_t bytes = bytes_g + it.n16 * (kBoxC * 128);
           const uint32_t buf = tile % kNumAcc;
-          mbar_wait(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u);
+          JEGAL_GTRACED(0, mbar_wait_lean(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kNMax;
 #pragma unroll 1
           for (int kb = 0; kb < kNumKBlocks; ++kb) {
             uint32_t need;
             const uint32_t off = base + ring.place(bytes, need);
-            mbar_wait(full(slot), phase);
+            JEGAL_GTRACED(1, mbar_wait_lean(full(slot), phase));
             tc_fence_after();
             const uint64_t dG = make_smem_desc_sw128(off);
             const uint64_t dC = make_smem_desc_sw128(off + bytes_g);
@@ -234,12 +346,22 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           umma_commit<1>(t_full(buf));
         }
       }
+      if (JEGAL_GTRACE_ON(p)) {
+        unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
+        g[2] = tr[0];
+        g[3] = tr[1];
+        g[4] = static_cast<unsigned long long>(clock64() - t_begin);
+      }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < kNormWarp0) {
     const int q = warp - 4;
     const int et = q * 32 + lane;  // frame within the row tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t tile = 0, parity = 0;
+    unsigned long long tr[4] = {0, 0, 0, 0};
+    const long long t_begin = JEGAL_GTRACE_ON(p) ? clock64() : 0;
+    (void)tr;
+    (void)t_begin;
     Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
     for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x, parity ^= 1u) {
       const Item it = nxt;
@@ -268,7 +390,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
       }
       for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
         const uint32_t buf = tile % kNumAcc;
-        mbar_wait(t_full(buf), (tile / kNumAcc) & 1u);
+        JEGAL_GTRACED(0, mbar_wait_lean(t_full(buf), (tile / kNumAcc) & 1u));
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_off + buf * kNMax;
         uint32_t v[kNMax];
@@ -285,9 +407,34 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           }
         }
         tmem_ld_wait();
+        if constexpr (kFuse != 0) {
+          // cos[t, w] = (g_t . c_w) / (max(||g_t||, eps) max(||c_w||, eps)): the row-norm warps summed the squares of
+          // the very bytes the MMAs consumed; 1 / max(sqrt(s), eps) = rsqrt(max(s, eps^2))
+          JEGAL_GTRACED(1, mbar_wait_lean(n_full(buf), (tile / kNumAcc) & 1u));
+          const float* sq = ssq + buf * kNormRows;
+          const float eps2 = p.row_eps * p.row_eps;
+          const float ig = rsqrtf(fmaxf(sq[et], eps2));
+          float* iw = inv_w + q * kNMax;
+          iw[lane] = rsqrtf(fmaxf(sq[128 + lane], eps2));
+          if (it.n16 > 2) iw[32 + lane] = rsqrtf(fmaxf(sq[160 + lane], eps2));
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < kNMax / 16; ++g) {
+            if (g < it.n16) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 ic = *reinterpret_cast<const float4*>(iw + g * 16 + j);
+                v[g * 16 + j] = __float_as_uint(__uint_as_float(v[g * 16 + j]) * ig * ic.x);
+                v[g * 16 + j + 1] = __float_as_uint(__uint_as_float(v[g * 16 + j + 1]) * ig * ic.y);
+                v[g * 16 + j + 2] = __float_as_uint(__uint_as_float(v[g * 16 + j + 2]) * ig * ic.z);
+                v[g * 16 + j + 3] = __float_as_uint(__uint_as_float(v[g * 16 + j + 3]) * ig * ic.w);
+              }
+            }
+          }
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty(buf));
+        if (lane == 0) mbar_arrive(t_empty(buf));  // also releases ssq[buf] to the row-norm warps (and orders inv_w reuse)
 
         const int32_t t = rt * 128 + et;
         const bool valid = t < it.T;
@@ -453,6 +600,102 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         }
       }
     }
+    if (JEGAL_GTRACE_ON(p) && q == 0 && lane == 0) {
+      unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
+      g[5] = tr[0];
+      g[6] = tr[1];
+      g[7] = static_cast<unsigned long long>(clock64() - t_begin);
+    }
+  }
+
+  if constexpr (kFuse != 0) {
+    if (warp >= kNormWarp0) {
+      // ---- row norms, fused into the load.  Norm warp kb owns k-block kb of every row tile: stage 8 * tile + kb.
+      // A stage is [frames: nb x 32 rows][words: n16 x 16 rows] of 128-byte swizzled lines, walked in units of
+      // 16 rows: lanes l and l + 16 share row l & 15, one takes the row's 16-byte chunks 0-3, the other 4-7
+      // (which one alternates with the row's parity), each in an order rotated by the row number, so the eight
+      // lanes of every shared-memory phase touch eight different bank groups.
+      constexpr bool kBf16 = kFuse == 2;
+      constexpr int kImpl = kFuse == 3 ? 0 : 1;
+      const int kb = warp - kNormWarp0;
+      const int r16 = lane & 15;
+      const int half = (r16 & 1) ^ (lane >> 4);
+      uint32_t lane_off[4];  // byte offset of this lane's four chunks inside a unit
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        lane_off[c] = static_cast<uint32_t>(r16) * 128u + static_cast<uint32_t>(half * 4 + ((c + (r16 >> 1)) & 3)) * 16u;
+      uint32_t tile = 0;
+      unsigned long long tr[4] = {0, 0, 0, 0};
+      const long long t_begin = JEGAL_GTRACE_ON(p) ? clock64() : 0;
+      (void)tr;
+      (void)t_begin;
+      RingAlloc ring;
+      Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
+      for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x) {
+        const Item it = nxt;
+        nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
+        for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
+          const int32_t rows = min(128, it.T - rt * 128);
+          const int32_t rows_g = ((rows + kBoxG - 1) / kBoxG) * kBoxG;
+          const int32_t nunits = (rows_g >> 4) + it.n16;  // <= 12
+          const uint32_t bytes = static_cast<uint32_t>(nunits) * 2048u;
+          // every role replays the same ring placement; this warp only touches its own stage
+          uint32_t my_off = 0;
+#pragma unroll
+          for (int k = 0; k < kNumKBlocks; ++k) {
+            uint32_t need;
+            const uint32_t o = ring.place(bytes, need);
+            if (k == kb) my_off = o;
+          }
+          const uint32_t stage = tile * kNumKBlocks + static_cast<uint32_t>(kb);
+          const uint32_t slot = stage % kGStages, phase = (stage / kGStages) & 1u;
+          const uint32_t a0 = base + my_off;
+          const uint32_t buf = tile % kNumAcc;
+          float* dst = ssq + buf * kNormRows;
+          // k-block 0 STORES its sums once the epilogue is done with the table's previous tile (no zeroing pass),
+          // the other seven add theirs behind it.  Four tiles of slack: these waits are almost never taken.
+          if (kb == 0) JEGAL_GTRACED(1, mbar_wait_lean(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u));
+          else JEGAL_GTRACED(1, mbar_wait_lean(z_full(buf), (tile / kNumAcc) & 1u));
+          JEGAL_GTRACED(0, mbar_wait_lean(full(slot), phase));
+          // a ROLLED loop over the stage's 16-row units (two in flight): the body is ~50 instructions and the
+          // kernel's hot code has to fit the instruction cache
+          uint32_t au = a0;
+          float* d = dst + r16;
+          const float* d_words = dst + 128 + r16 - rows_g;
+#pragma unroll 2
+          for (int32_t u = 0; u < nunits; ++u, au += 2048u) {
+            const uint4 x0 = lds128(au + lane_off[0]), x1 = lds128(au + lane_off[1]);
+            const uint4 x2 = lds128(au + lane_off[2]), x3 = lds128(au + lane_off[3]);
+            const float s0 = sumsq8<kBf16, kImpl>(x0, 0.f), s1 = sumsq8<kBf16, kImpl>(x1, 0.f);
+            const float s2 = sumsq8<kBf16, kImpl>(x2, 0.f), s3 = sumsq8<kBf16, kImpl>(x3, 0.f);
+            float ss = (s0 + s1) + (s2 + s3);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+            float* dd = const_cast<float*>(u * 16 < rows_g ? d + u * 16 : d_words + u * 16);
+            if (lane < 16) {
+              if (kb == 0) *dd = ss;
+              else atomicAdd(dd, ss);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty(slot));
+          if (lane == 0) {
+            if (kb == 0) mbar_arrive(z_full(buf));
+            mbar_arrive(n_full(buf));
+          }
+        }
+      }
+      if (JEGAL_GTRACE_ON(p) && lane == 0) {
+        unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
+        if (kb == 0) {
+          g[8] = tr[0];
+          g[9] = tr[1];
+          g[10] = static_cast<unsigned long long>(clock64() - t_begin);
+        } else if (kb == 7) {
+          g[11] = tr[0];
+          g[12] = tr[1];
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -462,7 +705,8 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
 
 constexpr size_t grouped_smem_bytes() {
   return 1024 + static_cast<size_t>(kGRingBytes) + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
-         2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + sizeof(uint32_t) * kGStages + 16;
+         2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + sizeof(uint32_t) * kGStages + 16 +
+         sizeof(float) * (kNumAcc * kNormRows + 4 * kNMax) + 8 * 2 * kNumAcc;  // kFuse: squared row norms, inverse word norms, 2 x 4 barriers
 }
 
 // one thread per group: softmax(scores / tau) within the group + first argmax
@@ -503,21 +747,54 @@ int make_grouped_maps(jegal_ctx* ctx, GroupedMaps* m, const void* gest_rows, int
   return JEGAL_OK;
 }
 
-template <int kEpi>
+template <int kEpi, int kFuse>
 int launch_grouped(jegal_ctx* ctx, const GroupedMaps& maps, const GroupedParams& p, cudaStream_t stream) {
-  auto kern = grouped_kernel<kEpi>;
+  auto kern = grouped_kernel<kEpi, kFuse>;
   constexpr size_t smem = grouped_smem_bytes();
-  constexpr uint32_t bit = 1u << (16 + kEpi);
+  constexpr uint32_t bit = 1u << (16 + kEpi + 2 * kFuse);
   if (!(ctx->smem_configured & bit)) {
     JEGAL_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ctx->smem_configured |= bit;
   }
   int grid = ctx->sm_count;
   if (p.n_items < grid) grid = p.n_items;
-  kern<<<grid, kGThreads, smem, stream>>>(maps, p);
+  const char* tr_env = std::getenv("JEGAL_GROUPED_TRACE");
+  if (tr_env && *tr_env == '1') {  // debug: per-role cycle accounting, printed to stderr (synchronises)
+    GroupedParams pt = p;
+    JEGAL_CUDA_OK(ctx, cudaMalloc(&pt.trace, sizeof(unsigned long long) * 16 * grid));
+    JEGAL_CUDA_OK(ctx, cudaMemsetAsync(pt.trace, 0, sizeof(unsigned long long) * 16 * grid, stream));
+    kern<<<grid, kFuse ? kGThreadsFuse : kGThreads, smem, stream>>>(maps, pt);
+    JEGAL_CUDA_OK(ctx, cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> h(static_cast<size_t>(16) * grid);
+    cudaMemcpy(h.data(), pt.trace, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost);
+    cudaFree(pt.trace);
+    double a[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 16; ++k) a[k] += static_cast<double>(h[static_cast<size_t>(16) * b + k]) / grid;
+    std::fprintf(stderr,
+                 "[grouped trace%s, mean cycles over %d CTAs, %d items] producer: wait empty %.0f of %.0f | mma: wait t_empty %.0f, "
+                 "wait full %.0f of %.0f | epilogue: wait t_full %.0f, wait norms %.0f of %.0f | norm warp 0: wait full %.0f, "
+                 "wait table %.0f of %.0f; norm warp 7: wait full %.0f, wait table %.0f\n",
+                 kFuse ? " (fused norms)" : "", grid, p.n_items, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+    ctx->launches++;
+    return JEGAL_OK;
+  }
+  kern<<<grid, kFuse ? kGThreadsFuse : kGThreads, smem, stream>>>(maps, p);
   JEGAL_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;
   return JEGAL_OK;
+}
+
+// kFuse: 0 operands are used as they are; 1 / 2 stored fp16 / bf16 rows, normalisation fused into the load
+// (3: fp16 with widen + FFMA arithmetic instead of FHFMA, an A/B knob: JEGAL_NORM_IMPL=0)
+template <int kEpi>
+int launch_grouped_any(jegal_ctx* ctx, int normalize_rows, int op_dtype, const GroupedMaps& maps, const GroupedParams& p,
+                       cudaStream_t stream) {
+  if (!normalize_rows) return launch_grouped<kEpi, 0>(ctx, maps, p, stream);
+  if (op_dtype == JEGAL_BF16) return launch_grouped<kEpi, 2>(ctx, maps, p, stream);
+  const char* e = std::getenv("JEGAL_NORM_IMPL");
+  if (e && *e == '0') return launch_grouped<kEpi, 3>(ctx, maps, p, stream);
+  return launch_grouped<kEpi, 1>(ctx, maps, p, stream);
 }
 
 }  // namespace
@@ -542,7 +819,7 @@ extern "C" {
 
 int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
                const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
-               const int32_t* word_idx_dev, float tau, float* heat_dev, float* full_heat_dev,
+               int normalize_rows, float row_eps, const int32_t* word_idx_dev, float tau, float* heat_dev, float* full_heat_dev,
                const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
                const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh, uint8_t* correct_dev,
                void* stream_) {
@@ -552,6 +829,9 @@ int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest
   if (gest_layout->n_clips != cont_layout->n_clips)
     return set_err(ctx, JEGAL_ERR_ARG, "spot: gesture and content layouts must hold the same clips");
   if (!(tau > 0.f)) return set_err(ctx, JEGAL_ERR_ARG, "spot: tau must be > 0");
+  if (normalize_rows && !(row_eps > 0.f)) return set_err(ctx, JEGAL_ERR_ARG, "spot: row_eps must be > 0");
+  if ((reinterpret_cast<uintptr_t>(gest_rows_dev) | reinterpret_cast<uintptr_t>(cont_rows_dev)) & 15u)
+    return set_err(ctx, JEGAL_ERR_ARG, "spot: operand rows must be 16-byte aligned");
   if (full_heat_dev && !full_off_dev) return set_err(ctx, JEGAL_ERR_ARG, "spot: full_heat needs full_off");
   if (correct_dev && (!win_lo_dev || !win_hi_dev)) return set_err(ctx, JEGAL_ERR_ARG, "spot: correct needs win_lo/win_hi");
   if (gest_layout->n_clips == 0) return JEGAL_OK;
@@ -573,15 +853,16 @@ int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest
   p.win_hi = win_hi_dev;
   p.thresh = thresh;
   p.correct = correct_dev;
+  p.row_eps = row_eps;
   GroupedMaps maps;
   rc = make_grouped_maps(ctx, &maps, gest_rows_dev, gest_layout->rows, cont_rows_dev, cont_layout->rows, op_dtype);
   if (rc != JEGAL_OK) return rc;
-  return launch_grouped<EPI_SPOT>(ctx, maps, p, static_cast<cudaStream_t>(stream_));
+  return launch_grouped_any<EPI_SPOT>(ctx, normalize_rows, op_dtype, maps, p, static_cast<cudaStream_t>(stream_));
 }
 
 int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,
                         const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
-                        int pool_mode, const float* gscale_dev, const float* cscale_dev,
+                        int normalize_rows, float row_eps, int pool_mode, const float* gscale_dev, const float* cscale_dev,
                         const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
                         int32_t group_size, float tau, float* scores_dev, float* probs_dev,
                         int32_t* argmax_dev, void* stream_) {
@@ -590,6 +871,9 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
   if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: bad op_dtype");
   if (pool_mode < 0 || pool_mode > 3) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: bad pool_mode");
   if (n_pairs < 0) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: negative n_pairs");
+  if (normalize_rows && !(row_eps > 0.f)) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: row_eps must be > 0");
+  if ((reinterpret_cast<uintptr_t>(gest_rows_dev) | reinterpret_cast<uintptr_t>(cont_rows_dev)) & 15u)
+    return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: operand rows must be 16-byte aligned");
   if (!pair_gest_dev && n_pairs > gest_layout->n_clips) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: n_pairs exceeds clips");
   if (!pair_cont_dev && n_pairs > cont_layout->n_clips) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: n_pairs exceeds clips");
   const bool want_groups = probs_dev || argmax_dev;
@@ -610,10 +894,11 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
   p.gscale = gscale_dev;
   p.cscale = cscale_dev;
   p.scores = scores_dev;
+  p.row_eps = row_eps;
   GroupedMaps maps;
   rc = make_grouped_maps(ctx, &maps, gest_rows_dev, gest_layout->rows, cont_rows_dev, cont_layout->rows, op_dtype);
   if (rc != JEGAL_OK) return rc;
-  rc = launch_grouped<EPI_POOL>(ctx, maps, p, stream);
+  rc = launch_grouped_any<EPI_POOL>(ctx, normalize_rows, op_dtype, maps, p, stream);
   if (rc != JEGAL_OK) return rc;
   if (want_groups) {
     const int32_t n_groups = n_pairs / group_size;

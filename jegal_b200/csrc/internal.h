@@ -122,6 +122,9 @@ int launch_rowinfo(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64
 int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int in_dtype,
                 int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows,
                 float* inv_meannorm, void* mean_rows, cudaStream_t stream);
+int launch_pair_cosine(jegal_ctx* ctx, const void* a_rows, const void* b_rows, int dtype, const int32_t* pair_a,
+                       const int32_t* pair_b, int32_t n_pairs, int normalize, float eps, float* scores,
+                       cudaStream_t stream);
 int launch_segmean(jegal_ctx* ctx, const void* x, int in_dtype, int32_t dim, const int32_t* seg_begin,
                    const int32_t* seg_end, int32_t n_seg, void* out, int out_dtype, int64_t ld_out,
                    int32_t col_off, cudaStream_t stream);

@@ -41,6 +41,12 @@ __device__ __forceinline__ void load8(const void* base, int64_t row, int col, fl
 
 template <int kOutDtype>
 __device__ __forceinline__ void store8(void* base, int64_t row, int col, const float (&x)[8]) {
+  if constexpr (kOutDtype == JEGAL_F32) {
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + row * kD + col);
+    p[0] = make_float4(x[0], x[1], x[2], x[3]);
+    p[1] = make_float4(x[4], x[5], x[6], x[7]);
+    return;
+  }
   uint32_t w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -97,8 +103,10 @@ prep_kernel(const void* __restrict__ emb, const int32_t* __restrict__ cu, int32_
           b[i] *= inv;
         }
       }
-      store8<kOutDtype>(out, r, lane * 8, a);
-      store8<kOutDtype>(out, r, 256 + lane * 8, b);
+      if (out != nullptr) {  // null: statistics only (jegal_clip_means), the rows are read and nothing is written back
+        store8<kOutDtype>(out, r, lane * 8, a);
+        store8<kOutDtype>(out, r, 256 + lane * 8, b);
+      }
     }
     if (want_mean) {
 #pragma unroll
@@ -158,6 +166,38 @@ __global__ void rowinfo_kernel(const int32_t* __restrict__ cu, int32_t n_clips, 
   }
 }
 
+// One warp per listed pair of 512-wide rows: dot product and both squared norms from one read of the two rows.
+// normalize: score = a.b / (max(||a||, eps) max(||b||, eps)) (nn.CosineSimilarity, evaluate_asd.py:45-47), else a.b
+template <int kDtype>
+__global__ void __launch_bounds__(256)
+pair_cosine_kernel(const void* __restrict__ a_rows, const void* __restrict__ b_rows, const int32_t* __restrict__ pair_a,
+                   const int32_t* __restrict__ pair_b, int32_t n_pairs, int normalize, float eps,
+                   float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int32_t pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pr >= n_pairs) return;
+  const int64_t ra = pair_a ? __ldg(pair_a + pr) : pr, rb = pair_b ? __ldg(pair_b + pr) : pr;
+  float a0[8], a1[8], b0[8], b1[8];
+  load8<kDtype>(a_rows, ra, lane * 8, a0);
+  load8<kDtype>(a_rows, ra, 256 + lane * 8, a1);
+  load8<kDtype>(b_rows, rb, lane * 8, b0);
+  load8<kDtype>(b_rows, rb, 256 + lane * 8, b1);
+  float dot = 0.f, sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dot += a0[i] * b0[i] + a1[i] * b1[i];
+    sa += a0[i] * a0[i] + a1[i] * a1[i];
+    sb += b0[i] * b0[i] + b1[i] * b1[i];
+  }
+  dot = warp_sum(dot);
+  if (normalize) {
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    dot = dot / (fmaxf(sqrtf(sa), eps) * fmaxf(sqrtf(sb), eps));
+  }
+  if (lane == 0) scores[pr] = dot;
+}
+
 template <int kIn>
 int launch_prep_in(jegal_ctx* ctx, int out_dtype, dim3 grid, cudaStream_t stream, const void* emb,
                    const int32_t* cu, int32_t n_clips, int normalize_rows, float row_eps,
@@ -167,6 +207,9 @@ int launch_prep_in(jegal_ctx* ctx, int out_dtype, dim3 grid, cudaStream_t stream
         emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm, mean_rows);
   } else if (out_dtype == JEGAL_F16) {
     prep_kernel<kIn, JEGAL_F16><<<grid, kPrepWarps * 32, 0, stream>>>(
+        emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm, mean_rows);
+  } else if (out_dtype == JEGAL_F32 && out == nullptr) {  // fp32 is a mean-row format only (clip_means)
+    prep_kernel<kIn, JEGAL_F32><<<grid, kPrepWarps * 32, 0, stream>>>(
         emb, cu, n_clips, normalize_rows, row_eps, mean_eps, out, inv_meannorm, mean_rows);
   } else {
     return set_err(ctx, JEGAL_ERR_ARG, "prep: out_dtype must be JEGAL_BF16 or JEGAL_F16");
@@ -197,6 +240,29 @@ int launch_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb, int
     default:
       return set_err(ctx, JEGAL_ERR_ARG, "prep: bad in_dtype");
   }
+}
+
+int launch_pair_cosine(jegal_ctx* ctx, const void* a_rows, const void* b_rows, int dtype, const int32_t* pair_a,
+                       const int32_t* pair_b, int32_t n_pairs, int normalize, float eps, float* scores,
+                       cudaStream_t stream) {
+  if (n_pairs <= 0) return JEGAL_OK;
+  const unsigned grid = static_cast<unsigned>((n_pairs + 7) / 8);
+  switch (dtype) {
+    case JEGAL_F32:
+      pair_cosine_kernel<JEGAL_F32><<<grid, 256, 0, stream>>>(a_rows, b_rows, pair_a, pair_b, n_pairs, normalize, eps, scores);
+      break;
+    case JEGAL_F16:
+      pair_cosine_kernel<JEGAL_F16><<<grid, 256, 0, stream>>>(a_rows, b_rows, pair_a, pair_b, n_pairs, normalize, eps, scores);
+      break;
+    case JEGAL_BF16:
+      pair_cosine_kernel<JEGAL_BF16><<<grid, 256, 0, stream>>>(a_rows, b_rows, pair_a, pair_b, n_pairs, normalize, eps, scores);
+      break;
+    default:
+      return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: bad dtype");
+  }
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
 }
 
 int launch_rowinfo(jegal_ctx* ctx, const int32_t* cu_dev, int32_t n_clips, int64_t rows,

@@ -137,6 +137,47 @@ def prep(
     return out, scale
 
 
+def clip_means(emb: torch.Tensor, layout: Layout, mean_eps: float = 1e-12, out_dtype: torch.dtype = torch.float32,
+               want_rows: bool = True, want_scale: bool = False):
+    """K0 without the row output (read-only pass): per clip the unit-norm mean row ([n_clips, 512] in
+    ``out_dtype``) and / or 1 / max(||mean||, mean_eps).  Returns (mean_rows | None, inv_meannorm | None)."""
+    _check_rows(emb, layout, "clip_means")
+    if emb.dtype not in _DT or out_dtype not in _DT:
+        raise JegalError("clip_means: unsupported dtype")
+    ctx = layout.ctx
+    rows = torch.empty((layout.n_clips, 512), dtype=out_dtype, device=emb.device) if want_rows else None
+    scale = torch.empty((layout.n_clips,), dtype=torch.float32, device=emb.device) if want_scale else None
+    if rows is None and scale is None:
+        raise JegalError("clip_means: nothing requested")
+    rc = ctx.lib.jegal_clip_means(ctx.h, layout.h, _ptr(emb), _DT[emb.dtype], float(mean_eps), _DT[out_dtype],
+                                  _ptr(rows), _ptr(scale), _stream())
+    ctx.check(rc, "jegal_clip_means")
+    return rows, scale
+
+
+def pair_cosine(a: torch.Tensor, b: torch.Tensor, pair_a: Optional[torch.Tensor] = None,
+                pair_b: Optional[torch.Tensor] = None, normalize: bool = True, eps: float = 1e-8,
+                n_pairs: Optional[int] = None) -> torch.Tensor:
+    """Cosine (or dot product) of listed pairs of 512-wide rows (nn.CosineSimilarity, evaluate_asd.py:45-47)."""
+    for t in (a, b):
+        if not t.is_cuda or t.dim() != 2 or t.shape[1] != 512 or not t.is_contiguous() or t.dtype not in _DT:
+            raise JegalError("pair_cosine: expected contiguous CUDA [n, 512] matrices")
+    if a.dtype != b.dtype:
+        raise JegalError("pair_cosine: both matrices must have the same dtype")
+    for t in (pair_a, pair_b):
+        if t is not None and (t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous()):
+            raise JegalError("pair_cosine: pair lists must be contiguous CUDA int32")
+    if n_pairs is None:
+        n_pairs = int(pair_a.numel() if pair_a is not None else pair_b.numel() if pair_b is not None
+                      else min(a.shape[0], b.shape[0]))
+    ctx = Context.get(a.device.index)
+    scores = torch.empty((n_pairs,), dtype=torch.float32, device=a.device)
+    rc = ctx.lib.jegal_pair_cosine(ctx.h, _ptr(a), a.shape[0], _ptr(b), b.shape[0], _DT[a.dtype], _ptr(pair_a),
+                                   _ptr(pair_b), n_pairs, int(bool(normalize)), float(eps), _ptr(scores), _stream())
+    ctx.check(rc, "jegal_pair_cosine")
+    return scores
+
+
 def simpool_allpairs(
     gest_rows: torch.Tensor,
     gest_layout: Layout,
@@ -231,8 +272,13 @@ def spot(
     win_lo: Optional[torch.Tensor] = None,
     win_hi: Optional[torch.Tensor] = None,
     thresh: float = 0.5,
+    normalize: bool = False,
+    row_eps: float = 1e-12,
 ) -> dict:
     """K3: word spotting over n clips (clip i of both layouts).
+
+    ``normalize=True``: the operands are the rows as stored (fp16 / bf16) and the kernel fuses
+    F.normalize (evaluate_spotting.py:49-50) into the load; False: rows are used as they are.
 
     Returns dict(heat [sum T] | None, full [sum T_i*W_i] | None, full_off int64 [n+1] | None,
     pred_frame int32 [n], pred_score fp32 [n], correct uint8 [n] | None).
@@ -240,7 +286,7 @@ def spot(
     _check_rows(gest_rows, gest_layout, "spot gest")
     _check_rows(cont_rows, cont_layout, "spot cont")
     if gest_rows.dtype != cont_rows.dtype or gest_rows.dtype not in (torch.bfloat16, torch.float16):
-        raise JegalError("spot: operands must both be bf16 or both fp16 (outputs of prep)")
+        raise JegalError("spot: operands must both be bf16 or both fp16 (stored rows or outputs of prep)")
     ctx = gest_layout.ctx
     n = gest_layout.n_clips
     dev = gest_rows.device
@@ -263,7 +309,7 @@ def spot(
         correct = torch.empty((n,), dtype=torch.uint8, device=dev)
     rc = ctx.lib.jegal_spot(
         ctx.h, gest_layout.h, _ptr(gest_rows), cont_layout.h, _ptr(cont_rows), _DT[gest_rows.dtype],
-        _ptr(word_idx), float(tau), _ptr(heat), _ptr(full), _ptr(full_off), _ptr(pred_frame), _ptr(pred_score),
+        int(bool(normalize)), float(row_eps), _ptr(word_idx), float(tau), _ptr(heat), _ptr(full), _ptr(full_off), _ptr(pred_frame), _ptr(pred_score),
         _ptr(win_lo), _ptr(win_hi), float(thresh), _ptr(correct), _stream(),
     )
     ctx.check(rc, "jegal_spot")
@@ -284,13 +330,15 @@ def simpool_pairs(
     tau: float = 0.07,
     want_probs: bool = False,
     n_pairs: Optional[int] = None,
+    normalize: bool = False,
+    row_eps: float = 1e-12,
 ) -> dict:
     """K4: pooled scores of listed (gesture clip, content clip) pairs, optional per-group
     softmax(score / tau) and argmax (groups of `group_size` consecutive pairs)."""
     _check_rows(gest_rows, gest_layout, "simpool_pairs gest")
     _check_rows(cont_rows, cont_layout, "simpool_pairs cont")
     if gest_rows.dtype != cont_rows.dtype or gest_rows.dtype not in (torch.bfloat16, torch.float16):
-        raise JegalError("simpool_pairs: operands must both be bf16 or both fp16 (outputs of prep)")
+        raise JegalError("simpool_pairs: operands must both be bf16 or both fp16 (stored rows or outputs of prep)")
     ctx = gest_layout.ctx
     dev = gest_rows.device
     for t in (pair_gest, pair_cont):
@@ -307,7 +355,8 @@ def simpool_pairs(
             probs = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
     rc = ctx.lib.jegal_simpool_pairs(
         ctx.h, gest_layout.h, _ptr(gest_rows), cont_layout.h, _ptr(cont_rows), _DT[gest_rows.dtype],
-        POOL_MODES[mode], _ptr(gscale), _ptr(cscale), _ptr(pair_gest), _ptr(pair_cont), n_pairs,
+        int(bool(normalize)), float(row_eps), POOL_MODES[mode], _ptr(gscale), _ptr(cscale), _ptr(pair_gest),
+        _ptr(pair_cont), n_pairs,
         max(group_size, 1), float(tau), _ptr(scores), _ptr(probs), _ptr(argmax), _stream(),
     )
     ctx.check(rc, "jegal_simpool_pairs")

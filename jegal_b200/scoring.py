@@ -35,7 +35,7 @@ TEMP = 0.07  # evaluate_spotting.py:39, evaluate_asd.py:43, plot_heatmap.py:34
 GROUPED_MAX_WORDS = 64  # K3 / K4 keep a clip's words on <= 64 accumulator columns; wider clips take the K1 route
 ArrayLike = Union[np.ndarray, torch.Tensor, Sequence]
 
-_layout_cache: Dict[bytes, Layout] = {}
+_layout_cache: Dict[Tuple[int, bytes], Layout] = {}
 
 
 class _Staging:
@@ -102,15 +102,16 @@ def _device() -> torch.device:
 
 
 def layout_for(lengths: Sequence[int]) -> Layout:
-    """Layouts are cached by their length vector (they own small device tables)."""
+    """Layouts are cached by (device, length vector): they own small device tables and a context bound to
+    the device that was current when they were made.  Least recently used entries go first."""
     arr = np.ascontiguousarray(np.asarray(lengths, dtype=np.int32))
-    key = arr.tobytes()
-    lay = _layout_cache.get(key)
+    key = (torch.cuda.current_device() if torch.cuda.is_available() else -1, arr.tobytes())
+    lay = _layout_cache.pop(key, None)
     if lay is None:
-        if len(_layout_cache) > 64:
-            _layout_cache.clear()
+        while len(_layout_cache) >= 64:
+            _layout_cache.pop(next(iter(_layout_cache)))
         lay = Layout.from_lengths(arr)
-        _layout_cache[key] = lay
+    _layout_cache[key] = lay  # (re)insert at the young end
     return lay
 
 
@@ -180,6 +181,24 @@ def _pack(x) -> PackedClips:
     return x if isinstance(x, PackedClips) else PackedClips.from_list(x)
 
 
+_NATIVE16 = (torch.float16, torch.bfloat16)
+
+
+def _stored_operands(x: PackedClips, normalize: bool, op_dtype: Optional[torch.dtype], fuse: bool = True):
+    """Operand rows for the grouped kernels (K3 / K4) and whether the KERNEL has to normalise them.
+
+    16-bit rows (what the reference's .pkl files hold) go to the kernel exactly as stored: the L2
+    normalisation is fused into the operand load, so no normalised copy is written to and re-read from HBM.
+    fp32 rows (or an explicit other ``op_dtype``, or ``fuse=False``) take one K0 pass: normalise + cast."""
+    if fuse and x.rows.dtype in _NATIVE16 and op_dtype in (None, x.rows.dtype):
+        return x.rows, bool(normalize)
+    od = op_dtype or (x.rows.dtype if x.rows.dtype in _NATIVE16 else torch.bfloat16)
+    if not normalize and x.rows.dtype == od:
+        return x.rows, False  # nothing to do: rows are used as stored
+    rows16, _ = ops.prep(x.rows, x.layout, normalize=normalize, out_dtype=od)
+    return rows16, False
+
+
 # ------------------------------------------------------------------------------ retrieval
 def get_similarity_matrix(emb1, emb2) -> torch.Tensor:
     """Drop-in for evaluation/evaluate_retrieval.py:38-48.
@@ -202,6 +221,11 @@ def _metrics_from_counts(n_greater: np.ndarray, n_equal: np.ndarray) -> dict:
     position whose value equals the diagonal: positions n_greater .. n_greater + n_equal - 1."""
     n_greater = n_greater.astype(np.int64)
     n_equal = n_equal.astype(np.int64)
+    if n_equal.size == 0:
+        raise JegalError("compute_metrics: empty similarity matrix")
+    if np.any(n_equal < 1):  # x[i, i] != x[i, i]: a NaN diagonal (zero-length clip or NaN embedding)
+        bad = np.flatnonzero(n_equal < 1)
+        raise JegalError(f"compute_metrics: the ground-truth score of row(s) {bad[:8].tolist()} is NaN")
     total = int(n_equal.sum())
     m = {}
     for k in (1, 5, 10, 25, 50):
@@ -255,8 +279,13 @@ def score_allpairs(gestures, contents, mode: str = "mean_mean", refnorm: bool = 
     if refnorm:
         if mode != "mean_mean":
             raise JegalError("refnorm applies to mode='mean_mean' only")
-        g16, gs = ops.prep(g.rows, g.layout, normalize=False, out_dtype=op_dtype, want_mean_scale=True)
-        c16, cs = ops.prep(c.rows, c.layout, normalize=False, out_dtype=op_dtype, want_mean_scale=True)
+        if g.rows.dtype == op_dtype and c.rows.dtype == op_dtype:  # stored rows are the operands: statistics only
+            (g16, c16) = (g.rows, c.rows)
+            gs, cs = ops.clip_means(g.rows, g.layout, want_rows=False, want_scale=True)[1], \
+                ops.clip_means(c.rows, c.layout, want_rows=False, want_scale=True)[1]
+        else:
+            g16, gs = ops.prep(g.rows, g.layout, normalize=False, out_dtype=op_dtype, want_mean_scale=True)
+            c16, cs = ops.prep(c.rows, c.layout, normalize=False, out_dtype=op_dtype, want_mean_scale=True)
     else:
         g16, gs = ops.prep(g.rows, g.layout, normalize=normalize_rows, out_dtype=op_dtype)
         c16, cs = ops.prep(c.rows, c.layout, normalize=normalize_rows, out_dtype=op_dtype)
@@ -269,8 +298,9 @@ def clip_similarity_matrix(gestures, contents, op_dtype: torch.dtype = torch.bfl
     two kernels: K0 emits the unit-norm mean row of every clip, K1 contracts them.
     Returns (n_gest, n_cont): cos(mean_g, mean_c)."""
     g, c = _pack(gestures), _pack(contents)
-    _, _, gm = ops.prep(g.rows, g.layout, normalize=False, out_dtype=op_dtype, want_mean_rows=True)
-    _, _, cm = ops.prep(c.rows, c.layout, normalize=False, out_dtype=op_dtype, want_mean_rows=True)
+    # read-only pass: the unit-norm mean rows are all that is written (n_clips x 1 KB)
+    gm, _ = ops.clip_means(g.rows, g.layout, out_dtype=op_dtype)
+    cm, _ = ops.clip_means(c.rows, c.layout, out_dtype=op_dtype)
     lg, lc = layout_for(np.ones(g.n, dtype=np.int32)), layout_for(np.ones(c.n, dtype=np.int32))
     s = ops.simpool_allpairs(gm, lg, cm, lc, "mean_mean")
     return s if device_out else s.cpu().numpy()
@@ -308,18 +338,28 @@ def _parse_wb(wb):
     return ast.literal_eval(wb) if isinstance(wb, str) else wb
 
 
+def _norm16(rows: torch.Tensor, normalize: bool, op_dtype: Optional[torch.dtype]) -> torch.Tensor:
+    """Normalised 16-bit rows of ONE clip for the K1 routes (one K0 launch)."""
+    od = op_dtype or (rows.dtype if rows.dtype in _NATIVE16 else torch.bfloat16)
+    if not normalize and rows.dtype == od:
+        return rows
+    return ops.prep(rows, layout_for([rows.shape[0]]), normalize=normalize, out_dtype=od)[0]
+
+
 def spot_batch(gestures, contents, word_idx: Sequence[int], temp: float = TEMP, normalize: bool = True,
                windows: Optional[Tuple[Sequence[int], Sequence[int]]] = None, thresh: float = 0.5,
-               want_full: bool = False, op_dtype: torch.dtype = torch.bfloat16) -> dict:
+               want_full: bool = False, op_dtype: Optional[torch.dtype] = None, fuse: bool = True,
+               want_heat: bool = True) -> dict:
     """All clips of a spotting set in one launch.  Returns numpy arrays:
     heat (list of (T_i,) target-word rows), full (list of (W_i, T_i) matrices) if asked,
-    pred_frame, pred_score and correct (if windows=(lo, hi) given)."""
+    pred_frame, pred_score and correct (if windows=(lo, hi) given).
+
+    fp16 (or bf16) embeddings are fed to K3 as stored and normalised inside the kernel; ``op_dtype`` /
+    ``fuse=False`` force the K0 pass (normalise + cast to ``op_dtype``) in front of it instead."""
     g, c = _pack(gestures), _pack(contents)
     if g.n != c.n:
         raise JegalError("spot_batch: gestures and contents must list the same clips")
     dev = g.rows.device
-    g16, _ = ops.prep(g.rows, g.layout, normalize=normalize, out_dtype=op_dtype)
-    c16, _ = ops.prep(c.rows, c.layout, normalize=normalize, out_dtype=op_dtype)
     word_idx = np.asarray(word_idx, dtype=np.int32)
     lo_h = hi_h = None
     if windows is not None:
@@ -337,38 +377,49 @@ def spot_batch(gestures, contents, word_idx: Sequence[int], temp: float = TEMP, 
     narrow = np.nonzero(lw <= GROUPED_MAX_WORDS)[0]
     if len(narrow):
         if len(wide) == 0:
-            gn16, cn16, gl_n, cl_n = g16, c16, g.layout, c.layout
+            gp, cp = g, c
         else:  # K3 takes clip i of both layouts: gather the rows of the narrow clips (one device gather each)
             keep = np.zeros(n, dtype=bool)
             keep[narrow] = True
-            gn16 = g16[torch.from_numpy(np.repeat(keep, lt)).to(dev)]
-            cn16 = c16[torch.from_numpy(np.repeat(keep, lw)).to(dev)]
-            gl_n, cl_n = layout_for(lt[narrow]), layout_for(lw[narrow])
+            gp = PackedClips(g.rows[torch.from_numpy(np.repeat(keep, lt)).to(dev)], layout_for(lt[narrow]))
+            cp = PackedClips(c.rows[torch.from_numpy(np.repeat(keep, lw)).to(dev)], layout_for(lw[narrow]))
+        g_op, kn_g = _stored_operands(gp, normalize, op_dtype, fuse)
+        c_op, kn_c = _stored_operands(cp, normalize, op_dtype, fuse)
+        if kn_g != kn_c or g_op.dtype != c_op.dtype:  # mixed storage types: normalise + cast both with K0
+            od = op_dtype or torch.bfloat16
+            g_op = ops.prep(gp.rows, gp.layout, normalize=normalize, out_dtype=od)[0]
+            c_op = ops.prep(cp.rows, cp.layout, normalize=normalize, out_dtype=od)[0]
+            kn_g = False
         wi = torch.as_tensor(word_idx[narrow], device=dev)
         lo = hi = None
         if windows is not None:
             lo, hi = torch.as_tensor(lo_h[narrow], device=dev), torch.as_tensor(hi_h[narrow], device=dev)
-        r = ops.spot(gn16, gl_n, cn16, cl_n, wi, tau=temp, want_heat=True, want_full=want_full,
-                     win_lo=lo, win_hi=hi, thresh=thresh)
-        cu_n = gl_n.cu_len
-        heat = r["heat"].cpu().numpy()
+        r = ops.spot(g_op, gp.layout, c_op, cp.layout, wi, tau=temp, want_heat=want_heat or not want_full,
+                     want_full=want_full, win_lo=lo, win_hi=hi, thresh=thresh, normalize=kn_g)
+        cu_n = gp.layout.cu_len
         pred_frame[narrow] = r["pred_frame"].cpu().numpy()
         pred_score[narrow] = r["pred_score"].cpu().numpy()
         if correct is not None:
             correct[narrow] = r["correct"].cpu().numpy().astype(bool)
+        if r["heat"] is not None:
+            heat = r["heat"].cpu().numpy()
+            for k_, i in enumerate(narrow):
+                heat_l[i] = heat[cu_n[k_]:cu_n[k_ + 1]]
         if want_full:
             full = r["full"].cpu().numpy()
             off = r["full_off"].cpu().numpy()
-        for k_, i in enumerate(narrow):
-            heat_l[i] = heat[cu_n[k_]:cu_n[k_ + 1]]
-            if want_full:
+            for k_, i in enumerate(narrow):
                 full_l[i] = full[off[k_]:off[k_ + 1]].reshape(int(lw[i]), int(lt[i]))
     for i in wide:
         # more words than the grouped kernel's 64 columns (a long transcript): the same arithmetic from K1's
         # plain-GEMM epilogue (frames x words cosines), the per-frame softmax over words and K2's first argmax
         T, W = int(lt[i]), int(lw[i])
-        cos = ops.simpool_allpairs(g16[cu_t[i]:cu_t[i + 1]], layout_for(np.ones(T, dtype=np.int32)),
-                                   c16[cu_w[i]:cu_w[i + 1]], layout_for(np.ones(W, dtype=np.int32)), "mean_mean")
+        g16 = _norm16(g.rows[cu_t[i]:cu_t[i + 1]], normalize, op_dtype)
+        c16 = _norm16(c.rows[cu_w[i]:cu_w[i + 1]], normalize, op_dtype if op_dtype is not None else g16.dtype)
+        if c16.dtype != g16.dtype:
+            g16 = _norm16(g.rows[cu_t[i]:cu_t[i + 1]], normalize, c16.dtype)
+        cos = ops.simpool_allpairs(g16, layout_for(np.ones(T, dtype=np.int32)),
+                                   c16, layout_for(np.ones(W, dtype=np.int32)), "mean_mean")
         probs, _ = ops.group_softmax(cos.view(-1), T, W, tau=temp)  # [T, W]: softmax over words for each frame
         row = probs[:, int(word_idx[i])].contiguous()
         v, f = ops.topk(row.view(1, T), 1)
@@ -414,20 +465,27 @@ def get_attn_matrix(*args, temp: float = TEMP):
     return r["full"][0], all_words
 
 
+def spot_targets(data_rows, word_boundaries, frame_thresh: int = 9):
+    """Per clip: index of the target word (first match, like list.index at evaluate_spotting.py:70) and the
+    accepted frame window [max(start - frame_thresh, 0), end + frame_thresh] (:75-78)."""
+    word_idx, lo, hi = [], [], []
+    for idx in range(len(word_boundaries)):
+        row = data_rows[idx]
+        twb = row.target_word_boundary if hasattr(row, "target_word_boundary") else row["target_word_boundary"]
+        twb = _parse_wb(twb)
+        allwb = _parse_wb(word_boundaries[idx])
+        word_idx.append(allwb.index(twb))
+        lo.append(max(twb[1] - frame_thresh, 0))
+        hi.append(twb[2] + frame_thresh)
+    return word_idx, lo, hi
+
+
 def get_spotting_acc(data_rows, gesture_emb, content_emb, word_boundaries, thresh: float = 0.5,
                      frame_thresh: int = 9) -> float:
     """Drop-in for evaluation/evaluate_spotting.py:59-90 — same arguments, same printed line,
     same returned accuracy (%), but one kernel launch for the whole set."""
     n = len(gesture_emb)
-    word_idx, lo, hi = [], [], []
-    for idx in range(n):
-        row = data_rows[idx]
-        twb = row.target_word_boundary if hasattr(row, "target_word_boundary") else row["target_word_boundary"]
-        twb = _parse_wb(twb)
-        allwb = _parse_wb(word_boundaries[idx])
-        word_idx.append(allwb.index(twb))  # first match, like list.index at :70
-        lo.append(max(twb[1] - frame_thresh, 0))
-        hi.append(twb[2] + frame_thresh)
+    word_idx, lo, hi = spot_targets(data_rows, word_boundaries, frame_thresh)
     r = spot_batch(gesture_emb, content_emb, word_idx, windows=(lo, hi), thresh=thresh)
     correct = int(r["correct"].sum())
     accuracy = (correct / n) * 100
@@ -439,64 +497,72 @@ def get_spotting_acc(data_rows, gesture_emb, content_emb, word_boundaries, thres
 def get_similarity_cos(query_emb, data_emb, temp: float = TEMP) -> np.ndarray:
     """Drop-in for evaluation/evaluate_asd.py:43-51: softmax over the P candidates of
     cos(query, candidate) / temp.  query_emb (1, 512), data_emb (P, 512) -> (P,) float32."""
-    q = _pack(_as_2d(query_emb))
-    d = _pack(_as_2d(data_emb))
-    if q.n != 1:
+    qa, da = _as_2d(query_emb), _as_2d(data_emb)
+    if qa.shape[0] != 1:
         raise JegalError("get_similarity_cos: query_emb must be (1, 512)")
-    # nn.CosineSimilarity clamps each norm at 1e-8 (evaluate_asd.py:45)
-    q16, _ = ops.prep(q.rows, q.layout, normalize=True, row_eps=1e-8)
-    d16, _ = ops.prep(d.rows, d.layout, normalize=True, row_eps=1e-8)
-    P = d.n
-    dev = q.rows.device
-    r = ops.simpool_pairs(d16, d.layout, q16, q.layout, torch.arange(P, dtype=torch.int32, device=dev),
-                          torch.zeros(P, dtype=torch.int32, device=dev), "mean_mean", group_size=P, tau=temp,
-                          want_probs=True)
-    return r["probs"].cpu().numpy()
+    if qa.dtype != da.dtype:
+        qa, da = qa.astype(np.float32), da.astype(np.float32)
+    dev = _device()
+    q = torch.from_numpy(np.ascontiguousarray(qa)).to(dev)
+    d = torch.from_numpy(np.ascontiguousarray(da)).to(dev)
+    P = d.shape[0]
+    # nn.CosineSimilarity clamps each norm at 1e-8 (evaluate_asd.py:45): one warp per candidate reads both rows
+    cos = ops.pair_cosine(d, q, None, torch.zeros(P, dtype=torch.int32, device=dev), normalize=True, eps=1e-8)
+    probs, _ = ops.group_softmax(cos, 1, P, tau=temp)
+    return probs.view(-1).cpu().numpy()
 
 
-def _pair_scores(g16, gl: Layout, c16, cl: Layout, pg: torch.Tensor, pc: torch.Tensor, pool: str,
-                 gs: Optional[torch.Tensor], cs: Optional[torch.Tensor]) -> torch.Tensor:
-    """Pooled scores of the listed pairs: K4 for pairs whose content clip has <= 64 words, K1 on the
-    single pair (any clip lengths) for the rest."""
+def _pair_scores(g: PackedClips, c: PackedClips, pg: torch.Tensor, pc: torch.Tensor, pool: str,
+                 op_dtype: Optional[torch.dtype] = None, fuse: bool = True) -> torch.Tensor:
+    """Pooled frame x word cosine scores of the listed pairs: K4 (row normalisation fused into the load for
+    16-bit stored rows) for content clips of <= 64 words, K1 on the single pair (any clip lengths) for the rest."""
+    gl, cl = g.layout, c.layout
+    dev = g.rows.device
     pc_h = pc.cpu().numpy()
-    wide = np.nonzero(cl.lengths[pc_h] > GROUPED_MAX_WORDS)[0] if pc_h.size else np.zeros(0, dtype=np.int64)
-    if len(wide) == 0:
-        return ops.simpool_pairs(g16, gl, c16, cl, pg, pc, pool, gscale=gs, cscale=cs)["scores"]
+    # K4 validates the WHOLE content layout (an unreferenced > 64-word clip would make it refuse the call),
+    # so the filtered route below is taken whenever the layout holds such a clip at all
+    if pc_h.size == 0 or cl.n_clips == 0 or int(cl.lengths.max()) <= GROUPED_MAX_WORDS:
+        g_op, kn = _stored_operands(g, True, op_dtype, fuse)
+        c_op, kn_c = _stored_operands(c, True, op_dtype, fuse)
+        if kn != kn_c or g_op.dtype != c_op.dtype:
+            od = op_dtype or torch.bfloat16
+            g_op, c_op, kn = ops.prep(g.rows, gl, out_dtype=od)[0], ops.prep(c.rows, cl, out_dtype=od)[0], False
+        return ops.simpool_pairs(g_op, gl, c_op, cl, pg, pc, pool, normalize=kn)["scores"]
+    wide = np.nonzero(cl.lengths[pc_h] > GROUPED_MAX_WORDS)[0]
     pg_h = pg.cpu().numpy()
-    scores = torch.empty((pg.numel(),), dtype=torch.float32, device=g16.device)
+    scores = torch.empty((pg.numel(),), dtype=torch.float32, device=dev)
     narrow = np.setdiff1d(np.arange(pg.numel()), wide)
     if len(narrow):
-        # K4 validates the whole content layout: hand it the <= 64-word clips only (one device gather)
         lw = cl.lengths
         keep = lw <= GROUPED_MAX_WORDS
         remap = np.cumsum(keep) - 1
-        cn16 = c16[torch.from_numpy(np.repeat(keep, lw)).to(g16.device)]
-        cs_n = None if cs is None else cs[torch.from_numpy(np.nonzero(keep)[0]).to(g16.device)].contiguous()
-        sel = torch.from_numpy(narrow).to(g16.device)
-        pc_n = torch.from_numpy(remap[pc_h[narrow]].astype(np.int32)).to(g16.device)
-        scores[sel] = ops.simpool_pairs(g16, gl, cn16, layout_for(lw[keep]), pg[sel].contiguous(), pc_n, pool,
-                                        gscale=gs, cscale=cs_n)["scores"]
+        cn = PackedClips(c.rows[torch.from_numpy(np.repeat(keep, lw)).to(dev)], layout_for(lw[keep]))
+        sel = torch.from_numpy(narrow).to(dev)
+        pc_n = torch.from_numpy(remap[pc_h[narrow]].astype(np.int32)).to(dev)
+        scores[sel] = _pair_scores(g, cn, pg[sel].contiguous(), pc_n, pool, op_dtype, fuse)
     cu_t, cu_w = gl.cu_len, cl.cu_len
     for p in wide:
         gi, ci = int(pg_h[p]), int(pc_h[p])
-        one = ops.simpool_allpairs(g16[cu_t[gi]:cu_t[gi + 1]], layout_for([cu_t[gi + 1] - cu_t[gi]]),
-                                   c16[cu_w[ci]:cu_w[ci + 1]], layout_for([cu_w[ci + 1] - cu_w[ci]]), pool,
-                                   gscale=None if gs is None else gs[gi:gi + 1],
-                                   cscale=None if cs is None else cs[ci:ci + 1])
+        g16 = _norm16(g.rows[cu_t[gi]:cu_t[gi + 1]], True, op_dtype)
+        c16 = _norm16(c.rows[cu_w[ci]:cu_w[ci + 1]], True, op_dtype if op_dtype is not None else g16.dtype)
+        if c16.dtype != g16.dtype:
+            g16 = _norm16(g.rows[cu_t[gi]:cu_t[gi + 1]], True, c16.dtype)
+        one = ops.simpool_allpairs(g16, layout_for([g16.shape[0]]), c16, layout_for([c16.shape[0]]), pool)
         scores[p] = one[0, 0]
     return scores
 
 
 def asd_batch(contents, gesture_tracks, pair_gest: Sequence[int], pair_cont: Sequence[int], tracks: int,
               prefixes: Sequence[int] = (2, 4, 6), temp: float = TEMP, mode: str = "reference",
-              op_dtype: torch.dtype = torch.bfloat16) -> dict:
+              op_dtype: Optional[torch.dtype] = None, fuse: bool = True) -> dict:
     """Active-speaker scoring for many groups at once (evaluate_asd.py:54-127).
 
     ``gesture_tracks`` / ``contents``: clip lists (or PackedClips); candidate p of the flat
     pair list scores gesture clip pair_gest[p] against content clip pair_cont[p]; every
     `tracks` consecutive pairs form one group whose first entry is the true speaker.
-    mode "reference": cosine of mean-pooled embeddings, as the reference; otherwise a
-    pooling mode name applied to the frame x word tile.
+    mode "reference": cosine of the mean-pooled embeddings, as the reference (one read-only pass over the
+    stored rows yields the clip means, one warp per pair their cosine); otherwise a pooling mode name applied
+    to the frame x word cosine tile (K4, row normalisation fused into the operand load).
     Returns dict(scores [n_groups, tracks], pred {P: int32 [n_groups]}, acc {P: float}).
     """
     g, c = _pack(gesture_tracks), _pack(contents)
@@ -504,14 +570,13 @@ def asd_batch(contents, gesture_tracks, pair_gest: Sequence[int], pair_cont: Seq
     pg = torch.as_tensor(np.asarray(pair_gest, dtype=np.int32), device=dev)
     pc = torch.as_tensor(np.asarray(pair_cont, dtype=np.int32), device=dev)
     if mode == "reference":
-        g16, gs = ops.prep(g.rows, g.layout, normalize=False, out_dtype=op_dtype, want_mean_scale=True, mean_eps=1e-8)
-        c16, cs = ops.prep(c.rows, c.layout, normalize=False, out_dtype=op_dtype, want_mean_scale=True, mean_eps=1e-8)
-        pool = "mean_mean"
+        # load_feats' emb.mean(axis=0) (evaluate_asd.py:31-36) + CosineSimilarity(eps=1e-8) (:45-47):
+        # cos = m_g . m_c / (max(||m_g||, eps) max(||m_c||, eps)) = dot of the two clamped-unit mean rows
+        gm, _ = ops.clip_means(g.rows, g.layout, mean_eps=1e-8)
+        cm, _ = ops.clip_means(c.rows, c.layout, mean_eps=1e-8)
+        scores = ops.pair_cosine(gm, cm, pg, pc, normalize=False)
     else:
-        g16, gs = ops.prep(g.rows, g.layout, out_dtype=op_dtype)
-        c16, cs = ops.prep(c.rows, c.layout, out_dtype=op_dtype)
-        pool = mode
-    scores = _pair_scores(g16, g.layout, c16, c.layout, pg, pc, pool, gs, cs)
+        scores = _pair_scores(g, c, pg, pc, mode, op_dtype, fuse)
     n_groups = pg.numel() // tracks
     pred, acc = {}, {}
     for P in prefixes:

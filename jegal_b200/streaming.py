@@ -32,10 +32,13 @@ def chunk_schedule(n_clips: int, chunk_clips: int, ramp: bool = True):
         c //= 2
     if n < 2 * c:
         return [n]
-    up = [c // 8, c // 8, c // 4, c // 2]
+    up = [max(1, c // 8), max(1, c // 8), max(1, c // 4)]
+    up.append(c - sum(up))  # the ramp sums to exactly one full chunk whatever c is (c // 8 * 8 != c in general)
     down = up[::-1]
-    mid = n - 2 * c
-    return up + [c] * (mid // c) + ([mid % c] if mid % c else []) + down
+    mid = n - sum(up) - sum(down)
+    sched = up + [c] * (mid // c) + ([mid % c] if mid % c else []) + down
+    assert sum(sched) == n and min(sched) > 0, (n, chunk_clips, sched)
+    return sched
 
 
 class StreamedGallery:
@@ -52,7 +55,10 @@ class StreamedGallery:
         cu = np.concatenate([[0], np.cumsum(self.lengths)])
         self.chunks = []
         lo = 0
-        for size in chunk_schedule(len(self.lengths), chunk_clips, ramp):
+        sched = chunk_schedule(len(self.lengths), chunk_clips, ramp)
+        if sum(sched) != len(self.lengths):
+            raise JegalError(f"StreamedGallery: chunk schedule covers {sum(sched)} of {len(self.lengths)} clips")
+        for size in sched:
             hi = lo + size
             self.chunks.append((lo, hi, int(cu[lo]), int(cu[hi]), ops.Layout.from_lengths(self.lengths[lo:hi])))
             lo = hi
@@ -144,6 +150,9 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
             gallery.stage[b][: r1 - r0].copy_(gallery.rows[r0:r1], non_blocking=True)
             gallery.copied[b].record(gallery.copy_stream)
 
+    # the staging buffers may still be read by the previous call's K0 on `main` (the function returns device
+    # tensors without synchronising): order this call's first copies behind everything enqueued so far
+    gallery.copy_stream.wait_stream(main)
     issue_copy(0)
     for c, (lo, hi, r0, r1, lay) in enumerate(gallery.chunks):
         b = c & 1

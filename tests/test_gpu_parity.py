@@ -648,3 +648,158 @@ def test_asd_with_a_content_track_of_more_than_64_words(dev, mode):
         else:
             want = float(oracle.simpool_allpairs([g], [c], mode)[0, 0])
         assert abs(r["scores"].reshape(-1)[p] - want) < TOL, (mode, p)
+
+
+# ----------------------------------------------------------------------------- normalisation fused into the load
+# Operands = the stored fp16 rows, exact in the tensor core; norms and scaling in fp32: the only differences to
+# the fp32 oracle are summation order and fp32 rounding, so the bars are far tighter than the bf16 ones.
+TOL_F16 = 2e-5
+PROB_TOL_F16 = 2e-4
+
+
+def _scaled_clips(n, lo, hi, seed, dtype=np.float16):
+    """Rows that are NOT unit-norm (norms 0.05 .. 20), so the fused normalisation has real work to do."""
+    rng = np.random.default_rng(seed + 1000)
+    out = []
+    for c in rand_clips(n, lo, hi, seed):
+        s = np.exp(rng.uniform(np.log(0.05), np.log(20.0), size=(len(c), 1))).astype(np.float32)
+        out.append((c.astype(np.float32) * s).astype(dtype))
+    return out
+
+
+@pytest.mark.parametrize("unit", [True, False])
+def test_spot_fused_normalisation_fp16_tight(dev, unit):
+    from jegal_b200 import ops, scoring
+    mk = rand_clips if unit else _scaled_clips
+    gest = mk(40, 1, 300, 140) + mk(3, 128, 128, 141) + mk(3, 1, 1, 142)
+    cont = mk(40, 1, 64, 143) + mk(3, 64, 64, 144) + mk(3, 1, 1, 145)
+    widx = [len(c) // 2 for c in cont]
+    gp, cp = scoring.PackedClips.from_list(gest), scoring.PackedClips.from_list(cont)  # (layouts launch a kernel)
+    launches0 = ops.Context.get().launches
+    r = scoring.spot_batch(gp, cp, widx, want_full=True)
+    assert ops.Context.get().launches - launches0 == 1, "stored fp16 rows must reach K3 without a K0 pass"
+    r_k0 = scoring.spot_batch(gp, cp, widx, want_full=True, fuse=False, op_dtype=torch.float16)
+    worst = 0.0
+    for i, (g_, c_) in enumerate(zip(gest, cont)):
+        a = oracle.get_attn_matrix(g_, c_)
+        worst = max(worst, float(np.abs(r["full"][i] - a).max()))
+        assert np.abs(r["full"][i] - a).max() < PROB_TOL_F16, i
+        assert np.abs(r["heat"][i] - a[widx[i]]).max() < PROB_TOL_F16
+        assert np.abs(r_k0["full"][i] - a).max() < PROB_TOL  # K0 rounds the normalised rows to fp16 once more
+        row = a[widx[i]]
+        assert abs(row[r["pred_frame"][i]] - row.max()) < PROB_TOL_F16 and abs(r["pred_score"][i] - row.max()) < PROB_TOL_F16
+    print(f"fused fp16 spotting: max |dp| = {worst:.2e}")
+
+
+def test_spot_fused_normalisation_golden_tight(dev, golden):
+    """The reference-executed golden heatmaps (tests/golden/spotting.npz) at the fp16-operand bar."""
+    from jegal_b200 import scoring
+    g = golden("spotting")
+    gest, cont = split(g["gest"], g["cu_t"]), split(g["cont"], g["cu_w"])
+    assert gest[0].dtype == np.float16
+    t = g["targets"]
+    lo, hi = np.maximum(t[:, 1] - 9, 0), t[:, 2] + 9
+    r = scoring.spot_batch(gest, cont, t[:, 0], windows=(lo, hi), want_full=True)
+    off = 0
+    n_checked = 0
+    for idx in range(len(gest)):
+        ref = g["attn"][off:off + r["full"][idx].size].reshape(r["full"][idx].shape)
+        off += ref.size
+        assert np.abs(r["full"][idx] - ref).max() < PROB_TOL_F16
+        row = ref[t[idx, 0]]
+        pred = int(np.argmax(row))
+        top2 = np.sort(row)[-2:] if len(row) > 1 else np.array([-1.0, row[0]])
+        if top2[1] - top2[0] > PROB_TOL_F16 and abs(row[pred] - 0.5) > PROB_TOL_F16:
+            assert r["pred_frame"][idx] == pred and bool(r["correct"][idx]) == bool(g["decisions"][idx])
+            n_checked += 1
+    assert n_checked > 0.9 * len(gest)
+
+
+def test_spot_fused_normalisation_bf16_storage_and_zero_rows(dev):
+    from jegal_b200 import ops
+    gest, cont = _scaled_clips(9, 20, 150, 150, np.float32), _scaled_clips(9, 2, 30, 151, np.float32)
+    gest[3][5] = 0.0  # a zero frame: F.normalize leaves it zero (x / max(0, eps)), cosines 0, uniform softmax
+    cont[4][1] = 0.0  # a zero word
+    gl, cl = ops.Layout.from_lengths([len(x) for x in gest]), ops.Layout.from_lengths([len(x) for x in cont])
+    for dt in (torch.bfloat16, torch.float16):
+        g_raw = torch.from_numpy(np.concatenate(gest)).to(dev).to(dt)
+        c_raw = torch.from_numpy(np.concatenate(cont)).to(dev).to(dt)
+        r = ops.spot(g_raw, gl, c_raw, cl, torch.zeros(9, dtype=torch.int32, device=dev), want_full=True, normalize=True)
+        full, off = r["full"].cpu().numpy(), r["full_off"].cpu().numpy()
+        g_h, c_h = g_raw.float().cpu().numpy(), c_raw.float().cpu().numpy()
+        for i in range(9):
+            a = oracle.get_attn_matrix(g_h[gl.cu_len[i]:gl.cu_len[i + 1]], c_h[cl.cu_len[i]:cl.cu_len[i + 1]])
+            got = full[off[i]:off[i + 1]].reshape(a.shape)
+            assert np.isfinite(got).all() and np.abs(got - a).max() < PROB_TOL_F16, (dt, i)
+        a3 = full[off[3]:off[4]].reshape(len(cont[3]), len(gest[3]))
+        assert np.allclose(a3[:, 5], 1.0 / len(cont[3]), atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", oracle.POOL_MODES)
+def test_simpool_pairs_fused_normalisation(dev, mode):
+    from jegal_b200 import ops
+    gest, cont = _scaled_clips(23, 1, 300, 160), _scaled_clips(17, 1, 64, 161)
+    rng = np.random.default_rng(162)
+    pg, pc = rng.integers(0, 23, 60).astype(np.int32), rng.integers(0, 17, 60).astype(np.int32)
+    gl, cl = ops.Layout.from_lengths([len(x) for x in gest]), ops.Layout.from_lengths([len(x) for x in cont])
+    g_raw = torch.from_numpy(np.concatenate(gest)).to(dev)
+    c_raw = torch.from_numpy(np.concatenate(cont)).to(dev)
+    r = ops.simpool_pairs(g_raw, gl, c_raw, cl, torch.from_numpy(pg).to(dev), torch.from_numpy(pc).to(dev), mode,
+                          group_size=4, want_probs=True, normalize=True)
+    ref = oracle.simpool_allpairs(gest, cont, mode)[pg, pc]
+    assert np.abs(r["scores"].cpu().numpy() - ref).max() < TOL_F16
+    probs = torch.softmax(torch.from_numpy(ref).view(-1, 4) / 0.07, dim=1).numpy()
+    assert np.abs(r["probs"].cpu().numpy().reshape(-1, 4) - probs).max() < PROB_TOL_F16
+    assert np.array_equal(r["argmax"].cpu().numpy(), ref.reshape(-1, 4).argmax(1))
+
+
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+def test_clip_means_and_pair_cosine(dev, dtype):
+    from jegal_b200 import ops
+    clips = [c.astype(dtype) for c in _scaled_clips(37, 1, 90, 170, np.float32)]
+    lay = ops.Layout.from_lengths([len(c) for c in clips])
+    rows = torch.from_numpy(np.concatenate(clips)).to(dev)
+    m32, sc = ops.clip_means(rows, lay, mean_eps=1e-8, want_scale=True)
+    ref_mean = np.stack([np.asarray(oracle.mean_pool(c), dtype=np.float32).reshape(512) for c in clips])
+    ref_norm = np.maximum(np.linalg.norm(ref_mean, axis=1), 1e-8)
+    np.testing.assert_allclose(sc.cpu().numpy(), 1.0 / ref_norm, rtol=2e-4 if dtype == np.float16 else 1e-5)
+    # fp16 inputs: numpy rounds the mean to fp16; the kernel mirrors that rounding, up to fp32 summation order
+    assert np.abs(m32.cpu().numpy() - ref_mean / ref_norm[:, None]).max() < (1e-3 if dtype == np.float16 else 1e-6)
+    m16, _ = ops.clip_means(rows, lay, out_dtype=torch.bfloat16)
+    assert (m16.float() - m32).abs().max().item() < 4e-3
+    # listed-pair cosine of raw rows (CosineSimilarity semantics incl. the 1e-8 clamp) and dot of unit rows
+    rng = np.random.default_rng(171)
+    pa, pb = rng.integers(0, 37, 200).astype(np.int32), rng.integers(0, 37, 200).astype(np.int32)
+    a = torch.from_numpy(ref_mean.astype(dtype)).to(dev)
+    a[5] = 0
+    got = ops.pair_cosine(a, a, torch.from_numpy(pa).to(dev), torch.from_numpy(pb).to(dev), normalize=True, eps=1e-8)
+    want = torch.nn.functional.cosine_similarity(a.float().cpu()[pa.astype(np.int64)], a.float().cpu()[pb.astype(np.int64)], dim=1, eps=1e-8)
+    assert (got.cpu() - want).abs().max().item() < 2e-6
+    dots = ops.pair_cosine(m32, m32, torch.from_numpy(pa).to(dev), torch.from_numpy(pb).to(dev), normalize=False)
+    assert (dots.cpu() - (m32.cpu()[pa.astype(np.int64)] * m32.cpu()[pb.astype(np.int64)]).sum(1)).abs().max().item() < 2e-6
+
+
+def test_asd_reference_mode_launches_no_tile_kernel(dev, golden):
+    """evaluate_asd's score is cos(mean, mean): two read-only passes for the clip means + one warp per pair,
+    not a T x W tile through the tensor cores; results at the fp32 bar against the reference-executed golden."""
+    from jegal_b200 import ops, scoring
+    g = golden("asd")
+    tracks = int(g["tracks"])
+    gest, cont = split(g["gest"], g["cu_t"]), split(g["cont"], g["cu_w"])
+    n_groups = len(gest) // tracks
+    pair_g = np.arange(n_groups * tracks)
+    pair_c = np.repeat(np.arange(n_groups) * tracks, tracks)
+    gp, cp = scoring.PackedClips.from_list(gest), scoring.PackedClips.from_list(cont)
+    l0 = ops.Context.get().launches
+    r = scoring.asd_batch(cp, gp, pair_g, pair_c, tracks)
+    assert ops.Context.get().launches - l0 == 2 + 1 + 3  # clip means x2, pair cosine, argmax for 2 / 4 / 6 candidates
+    for pi, p in enumerate((2, 4, 6)):
+        for grp in range(n_groups):
+            pos = grp * tracks
+            q = oracle.asd_mean_emb(cont[pos])
+            allg = torch.cat([oracle.asd_mean_emb(gest[pos + k]) for k in range(p)])
+            cos = torch.nn.functional.cosine_similarity(q, allg, dim=1).numpy()
+            assert np.abs(r["scores"][grp, :p] - cos).max() < 1e-3  # fp16 rounding of numpy's mean, mirrored
+            if r["pred"][p][grp] != g["preds"][grp, pi]:
+                assert abs(cos[r["pred"][p][grp]] - cos[g["preds"][grp, pi]]) < 1e-3
+        assert abs(r["acc"][p] - g["accuracy"][pi]) <= 1.0 / n_groups + 1e-9

@@ -290,7 +290,12 @@ def test_wordlevel_range_logic_against_reference_golden(golden, monkeypatch):
 
 def test_streaming_chunk_schedule():
     from jegal_b200.streaming import chunk_schedule
-    for n, c in [(8192, 2048), (65536, 8192), (301, 64), (100, 64), (5, 64), (4096, 2048), (10000, 2048), (0, 64), (130, 64)]:
+    cases = [(8192, 2048), (65536, 8192), (301, 64), (100, 64), (5, 64), (4096, 2048), (10000, 2048), (0, 64), (130, 64),
+             # chunk sizes that are not multiples of 8 / 64 (3 GPUs, odd galleries): the ramps must still sum to a chunk
+             (1000, 1000), (65536, 100), (65536, 8191), (21846, 2730), (50000, 6250), (999, 77), (257, 65), (12345, 1543)]
+    rng = np.random.default_rng(0)
+    cases += [(int(rng.integers(1, 200000)), int(rng.integers(1, 20000))) for _ in range(300)]
+    for n, c in cases:
         sch = chunk_schedule(n, c)
         assert sum(sch) == n and all(x > 0 for x in sch) and max(sch, default=0) <= max(c, n if n < 128 else c)
         if len(sch) >= 8:  # ramps up at the start, down at the end
