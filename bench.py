@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the JEGAL cross-modal scoring path on B200 (contract: see the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg2|cfg3|cfg4]
 
 One "step" = one pass of the hot path over one batch of synthetic embeddings:
     raw fp16 embeddings -> K0 normalise+cast -> K1 fused T x W cosine + pooling (tcgen05)
@@ -12,17 +12,25 @@ are quoted on; it fits one GPU): 1000 query clips (T = 64 frames) against a 65 5
 gallery (W = 16 words), D = 512, pooling max over frames then mean over words, top-10.
 The gallery is sharded by clip over the N GPUs (strong scaling: total work is fixed).
 
+With N > 1 every rank materialises its slice of the SAME seeded, planted gallery (synth.cfg5_sharded), and the line
+carries `recall_at_1_planted` and `topk_checksum` (CRC-32 of the merged top-k indices): they must equal the N = 1 values.
+The timed region is extended to >= --min-seconds (default 2 s) so that every N reports sustained clocks, not a burst.
+The default line also folds in `stages`: every kernel of the path once at its BASELINE config size (bench_stages.py).
+--workload cfg2|cfg3|cfg4 benches the other BASELINE.json configurations through the same contract (N > 1: replicas).
+
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -130,12 +138,21 @@ def cpu_simpool_topk(q: torch.Tensor, g: torch.Tensor, Q: int, T: int, G: int, W
     return oracle.topk(out.numpy(), k)
 
 
+def use_all_cores():
+    """The CPU legs use every host core, whatever NUMA binding the GPU arm chose."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except Exception:
+        pass
+    torch.set_num_threads(os.cpu_count() or 1)
+
+
 def run_cpu_sample(wl: dict, g_sample: int, steps: int, warmup: int):
     """Time the CPU port on `g_sample` gallery clips per step (same queries, same shapes)."""
     from jegal_b200 import synth
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    q, g, _ = synth.cfg5_gallery(wl["Q"], g_sample, wl["T"], wl["W"], seed=1239, device="cpu")
+    use_all_cores()
+    q, g, _ = synth.cfg5_sharded(wl["Q"], g_sample, wl["T"], wl["W"], seed=1239, device="cpu")
     for _ in range(warmup):
         cpu_simpool_topk(q, g, wl["Q"], wl["T"], g_sample, wl["W"], wl["mode"], wl["k"])
     t0 = time.perf_counter()
@@ -148,18 +165,37 @@ def run_cpu_sample(wl: dict, g_sample: int, steps: int, warmup: int):
 def main_reference(args, wl, rank, world):
     if rank != 0:
         return
-    g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 4096))
     cores = os.cpu_count() or 1
-    value, dt = run_cpu_sample(wl, g_sample, args.steps, args.warmup)
-    sample = (f"{wl['Q']} queries x {g_sample} gallery clips per step (same T/W/D/pooling/top-k), "
-              f"fp32 torch CPU, {torch.get_num_threads()} threads")
+    note = ("the reference is pure Python/torch-CPU and cannot travel to the GPU box; this arm times the oracle port of its "
+            "scoring arithmetic on the host cores")
+    if args.workload == "cfg5":
+        g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 4096))
+        value, dt = run_cpu_sample(wl, g_sample, args.steps, args.warmup)
+        desc = wl["desc"]
+        sample = (f"{wl['Q']} queries x {g_sample} gallery clips per step (same T/W/D/pooling/top-k), "
+                  f"fp32 torch CPU, {torch.get_num_threads()} threads")
+        extra = {}
+    else:
+        import bench_stages
+
+        use_all_cores()
+        # a bounded sample of the workload (the per-clip / per-group rate does not depend on the set size)
+        n_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_N", {"cfg2": 1000, "cfg3": 4000, "cfg4": 2000}[args.workload]))
+        w = bench_stages.WORKLOADS[args.workload]("cpu", n_sample, cpu_only=True)
+        budget = float(os.environ.get("JEGAL_CPU_BUDGET_S", 10.0))
+        for _ in range(min(args.warmup, 1)):
+            w.cpu_reference(budget_s=1.0)
+        vals = [w.cpu_reference(budget_s=budget) for _ in range(max(1, args.steps))]
+        value = float(np.mean([v["value"] for v in vals]))
+        dt = float(np.mean([v["seconds"] for v in vals]))
+        desc, sample = w.desc, vals[0]["sample"]
+        extra = {k: v for k, v in vals[0].items() if k not in ("value", "seconds", "sample")}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "note": "the reference is pure Python/torch-CPU and cannot travel to "
-                   "the GPU box; this arm times the oracle port of its scoring arithmetic on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "strong" if args.workload == "cfg5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "note": note},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,48 +203,73 @@ def main_reference(args, wl, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa(local_rank: int):
+    """Run this rank's host threads (and place its pinned buffers) on the CPUs next to its GPU: eight ranks
+    pulling 134 MB each through one socket's memory was the N = 8 end-to-end bottleneck of round 1."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def sync_all(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed_steps(args, world, dev, est_ms: float) -> int:
+    """K steps as asked, extended so that the timed region lasts >= --min-seconds on every N (same count on all ranks)."""
+    t = torch.tensor([est_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    need = int(math.ceil(args.min_seconds * 1e3 / max(float(t[0]), 1e-3))) if args.min_seconds > 0 else 0
+    return max(args.steps, need)
+
+
 def main_ours(args, wl, rank, local_rank, world):
-    from jegal_b200 import ops, sharded, synth
+    from jegal_b200 import ops, sharded, streaming, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     ctx = ops.Context.get(local_rank)
     Q, T, G, W, mode, k = wl["Q"], wl["T"], wl["G"], wl["W"], wl["mode"], wl["k"]
     weak = args.scaling == "weak"
     G_total = G * world if weak else G
 
-    # synthetic embeddings, generated on the device (identical on every rank: same seed)
+    # the same seeded, planted gallery at every N: each rank materialises its clip range, rank 0 the queries too
     lo, hi = sharded.shard_range(G_total, rank, world)
-    q_raw, g_all, gt = synth.cfg5_gallery(Q, G_total, T, W, seed=1239, device=dev) if world == 1 else (None, None, None)
-    if world > 1:
-        # every rank generates only what it owns: queries on rank 0, its own gallery shard
-        q_full, _, _ = synth.cfg5_gallery(Q, 16, T, W, seed=1239, device=dev)
-        gen = torch.Generator(device=dev).manual_seed(1239 + 1000 * (rank + 1))
-        g_shard = torch.nn.functional.normalize(
-            torch.randn(((hi - lo) * W, 512), device=dev, generator=gen), dim=-1).half()
-        q_raw = q_full if rank == 0 else torch.empty_like(q_full)
-    else:
-        g_shard = g_all
+    q_raw, g_shard, gt = synth.cfg5_sharded(Q, G_total, T, W, seed=1239, device=dev, lo=lo, hi=hi, want_queries=(rank == 0))
+    if q_raw is None:
+        q_raw = torch.empty((Q * T, 512), dtype=torch.float16, device=dev)
     n_shard = hi - lo
     q_layout = ops.Layout.from_lengths([T] * Q)
     s_layout = ops.Layout.from_lengths([W] * n_shard)
     q16 = torch.empty((Q * T, 512), dtype=torch.bfloat16, device=dev)
     g16 = torch.empty((n_shard * W, 512), dtype=torch.bfloat16, device=dev)
     scores = torch.empty((Q, n_shard), dtype=torch.float32, device=dev)
-    ev_k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-             for _ in range(args.steps)]
-
     ex = ops.TopkExchange(Q, k) if (world > 1 and args.exchange == "p2p") else None
 
-    def step(i_timed=None):
+    def step(ev=None):
         qr = sharded.broadcast_queries(q_raw, Q * T, torch.float16, dev) if world > 1 else q_raw
         ops.prep(qr, q_layout, out=q16)
         ops.prep(g_shard, s_layout, out=g16)
-        if i_timed is not None:
-            ev_k1[i_timed][0].record()
+        if ev is not None:
+            ev[0].record()
         ops.simpool_allpairs(q16, q_layout, g16, s_layout, mode, out=scores)
-        if i_timed is not None:
-            ev_k1[i_timed][1].record()
+        if ev is not None:
+            ev[1].record()
         if ex is not None:
             return ex.topk(scores, idx_offset=lo)  # K2 + NVLink exchange + merge, two kernels
         v, i = ops.topk(scores, k, idx_offset=lo)
@@ -220,25 +281,28 @@ def main_ours(args, wl, rank, local_rank, world):
             v, i = ops.topk_merge(vals.view(world, Q, k), idxs.view(world, Q, k))
         return v, i
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm - 1):
         step()
-    sync_all()
+    sync_all(world)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    step()
+    w1.record()
+    sync_all(world)
+    n_steps = timed_steps(args, world, dev, w0.elapsed_time(w1))
+    ev_k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
+    sync_all(world)
     e0.record()
-    for s in range(args.steps):
-        v, i = step(s)
+    for s in range(n_steps):
+        v, i = step(ev_k1[s])
     e1.record()
-    sync_all()
+    sync_all(world)
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
@@ -249,25 +313,23 @@ def main_ours(args, wl, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lc, op=dist.ReduceOp.SUM)
     ms_total, k1_ms = float(t[0]), float(t[1])
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / n_steps
     value = Q * G_total / (ms_step * 1e-3)
+    idx_host = i.cpu().numpy()
+    val_host = v.cpu().numpy()
 
     # ---- end to end through the public host API: pinned host buffers in, top-k on the host out.
     # jegal_b200.streaming overlaps the H2D copy of gallery chunk i+1 with K0/K1/K2 on chunk i.
-    from jegal_b200 import streaming
-
-    q_host = q_raw.cpu().pin_memory() if rank == 0 or world == 1 else None
+    q_host = q_raw.cpu().pin_memory() if rank == 0 else None
     gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), chunk_clips=max(2048, n_shard // 8),
                                         device=dev, idx_base=lo)
-    e2e_steps = max(3, min(args.steps, 10))
-    h2d = gallery.nbytes + (Q * T * 512 * 2 if (rank == 0 or world == 1) else 0)
+    h2d = gallery.nbytes + (Q * T * 512 * 2 if rank == 0 else 0)
     d2h = Q * k * 8
 
     def e2e_step():
         # queries start in rank 0's pinned host memory; they are copied (and with several GPUs broadcast) in 4
         # parts, pipelined with the scoring of the first gallery chunk (jegal_b200.streaming)
-        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode,
-                                                  q_parts=4,
+        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_parts=4,
                                                   bcast_src=0 if world > 1 else None)
         if world > 1:
             vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
@@ -277,16 +339,22 @@ def main_ours(args, wl, rank, local_rank, world):
             vv, ii = ops.topk_merge(vals.view(world, Q, k), idxs.view(world, Q, k))
         return vv.cpu(), ii.cpu()  # device->host read of the step's result (synchronises)
 
-    if args.no_e2e:
-        e2e_steps = 0
-        e2e_dt = float("nan")
-    else:
+    e2e_steps, e2e_dt, hi_ = 0, float("nan"), None
+    if not args.no_e2e:
         e2e_step()
-        sync_all()
+        sync_all(world)
+        t0 = time.perf_counter()
+        e2e_step()
+        sync_all(world)
+        est = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(est, op=dist.ReduceOp.MAX)
+        e2e_steps = max(3, min(n_steps, int(math.ceil(min(args.min_seconds, 1.0) * 1e3 / max(float(est[0]), 1e-3)))))
+        sync_all(world)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             hv, hi_ = e2e_step()
-        sync_all()
+        sync_all(world)
         e2e_dt = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     hb = torch.tensor([h2d], dtype=torch.int64, device=dev)
@@ -297,32 +365,42 @@ def main_ours(args, wl, rank, local_rank, world):
 
     if rank != 0:
         return
-    # sanity: with one GPU the planted matches must be retrieved (the bench measures real work)
-    recall1 = None
-    if world == 1 and gt is not None:
-        recall1 = float((i[:, 0].cpu().numpy() == gt).mean())
-        if not args.no_e2e:  # the streamed host path must return the very same lists
-            assert np.array_equal(hi_.numpy(), i.cpu().numpy()), "e2e top-k differs from the resident path"
+    # result check at EVERY N: the planted matches are the top-1, and the merged lists are those of the 1-GPU run
+    recall1 = float((idx_host[:, 0] == gt).mean())
+    checksum = zlib.crc32(np.ascontiguousarray(idx_host.astype(np.int32)).tobytes())
+    val_checksum = zlib.crc32(np.ascontiguousarray(val_host.astype(np.float32)).tobytes())
+    e2e_same = None
+    if hi_ is not None:  # the streamed host path must return the very same lists
+        e2e_same = bool(np.array_equal(hi_.numpy(), idx_host))
+        assert e2e_same, "e2e top-k differs from the resident path"
     peaks = load_peaks()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "k1_traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic_r02.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic_r01.json")
     if world == 1 and os.path.exists(tpath):  # from the committed ncu --set full capture of this very launch shape
         with open(tpath) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]
     flops = 2.0 * 512 * (Q * T) * (n_shard * W)  # algorithmic flops of ONE K1 launch on this rank's shard
     achieved = flops / (k1_ms * 1e-3) / 1e12
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n_steps, "steps_requested": args.steps,
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": wl["desc"] + (f"; gallery x{world} (weak)" if weak else "; gallery sharded by clip over the GPUs"),
+            "workload": wl["desc"],
+            "sharding": f"gallery x{world} (weak)" if weak else "gallery sharded by clip over the GPUs (strong scaling)",
             "step": "K0 prep(queries)+K0 prep(gallery shard)+K1 fused sim-pool+K2 top-k" + (
                 "" if world == 1 else "+NVLink peer-memory exchange+merge (fused, csrc/exchange.cu)" if ex is not None
                 else "+NCCL all-gather+merge"),
             "inputs": "raw fp16 unit-norm embeddings resident in HBM; bf16 operands, fp32 accumulate in TMEM",
             "l2": "no flush needed: the 1.07 GB gallery (>= 134 MB per shard) exceeds the 126 MB L2 every step",
-            "parallelism": f"gallery-sharded x{world}", "recall_at_1_planted": recall1,
+            "timed_region": f"{n_steps} steps = {ms_total / 1e3:.2f} s (extended from --steps {args.steps} to last >= {args.min_seconds} s)",
+            "parallelism": f"gallery-sharded x{world}",
+            "data_check": "the same seeded, planted gallery at every N (each rank materialises its clip range); "
+                          "recall_at_1_planted and topk_checksum must equal the N = 1 values",
+            "recall_at_1_planted": recall1, "topk_checksum": checksum, "topk_value_checksum": val_checksum,
+            "e2e_topk_equals_resident": e2e_same, "numa_bound_cpus": numa_cpus,
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": d2h,
@@ -334,8 +412,17 @@ def main_ours(args, wl, rank, local_rank, world):
                      "frac_of_sustained": achieved / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None,
                      "peak_source": peaks["source"] + ", burst bf16 figure", "k1_ms": k1_ms,
                      "algorithmic_flops_per_launch": flops, "traffic": traffic,
-                     "traffic_unit": "bytes (dram read+write per launch, ncu; profiles/k1_traffic_r01.json)"},
+                     "traffic_unit": f"bytes (dram read+write per launch, ncu; {os.path.relpath(tpath, ROOT)})"},
     }
+    if world == 1 and not args.no_stages:
+        import bench_stages
+
+        del gallery, scores, g16, q16, g_shard
+        torch.cuda.empty_cache()
+        try:
+            line["stages"] = bench_stages.stage_table(dev, peaks)
+        except Exception as e:  # the stage table must never cost the headline line
+            line["stages"] = [{"error": repr(e)[:300]}]
     if world == 1 and not args.no_cpu:
         g_sample = int(os.environ.get("JEGAL_CPU_SAMPLE_G", 4096))
         n_rep = 3
@@ -347,20 +434,123 @@ def main_ours(args, wl, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def main_workload(args, rank, local_rank, world):
+    """BASELINE.json configs 2-4 through the same contract.  Their units (clips, groups, clip pairs) are independent,
+    so N > 1 runs one replica of the workload per GPU on its own seeded set: weak scaling, no collective."""
+    import bench_stages
+    from jegal_b200 import ops
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa(local_rank)
+    ctx = ops.Context.get(local_rank)
+    w = bench_stages.WORKLOADS[args.workload](dev, rank=rank)
+    warm = max(args.warmup, 3)
+    for _ in range(warm - 1):
+        w.step()
+    sync_all(world)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    w.step()
+    w1.record()
+    sync_all(world)
+    n_steps = timed_steps(args, world, dev, w0.elapsed_time(w1))
+    n_ev = min(n_steps, 2000)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all(world)
+    e0.record()
+    for s in range(n_steps):
+        w.step(evs[s] if s < n_ev else None)
+    e1.record()
+    sync_all(world)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dom_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    t = torch.tensor([e0.elapsed_time(e1), dom_ms], dtype=torch.float64, device=dev)
+    lc = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lc, op=dist.ReduceOp.SUM)
+    ms_step, dom_ms = float(t[0]) / n_steps, float(t[1])
+    value = w.units * world / (ms_step * 1e-3)
+    # ---- end to end: pinned host rows in, decisions / metrics on the host out
+    e2e_steps, e2e_dt = 0, float("nan")
+    if not args.no_e2e:
+        w.e2e_setup()
+        w.e2e_step()
+        sync_all(world)
+        t0 = time.perf_counter()
+        w.e2e_step()
+        torch.cuda.synchronize()
+        est = time.perf_counter() - t0
+        e2e_steps = max(3, min(50, int(math.ceil(min(args.min_seconds, 1.0) / max(est, 1e-4)))))
+        sync_all(world)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            w.e2e_step()
+        sync_all(world)
+        e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    work = w.roofline_work()
+    if w.bound == "tensor":
+        achieved, peak, unit = work / (dom_ms * 1e-3) / 1e12, peaks["tflops"], "TFLOP/s"
+    else:
+        achieved, peak, unit = work / (dom_ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n_steps, "steps_requested": args.steps,
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": w.dtype, "data": "synthetic",
+        "config": {"workload": w.desc, "parallelism": "single GPU" if world == 1 else f"{world} replicas (independent units, no collective)",
+                   "inputs": "stored fp16 unit-norm embeddings resident in HBM",
+                   "l2": "no flush needed: the operands of one step exceed the 126 MB L2" if args.workload != "cfg2"
+                         else "cfg2's operands (138 MB) are about the size of the L2; the step is tensor-bound",
+                   "parity": w.parity()},
+        "clocks": clocks,
+        "e2e": {"value": w.units * world / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(w.h2d_bytes) * world,
+                "d2h_bytes_per_step": int(w.d2h_bytes) * world, "ms_per_step": float(te[0]) * 1e3, "steps": e2e_steps,
+                "path": "pinned host fp16 rows (packed clip index layout) -> chunked H2D overlapped with the kernels -> decisions / "
+                        "rank counts -> host (jegal_b200.streaming)"},
+        "gpu_launches": int(lc[0]),
+        "roofline": {"bound": w.bound, "kernel": w.kernel, "achieved": achieved, "peak": peak, "unit": unit,
+                     "frac": achieved / peak, "kernel_ms": dom_ms, "algorithmic_work_per_launch": work,
+                     "peak_source": peaks["source"], "traffic": None},
+    }
+    if world == 1 and not args.no_cpu:
+        use_all_cores()
+        c = w.cpu_reference(budget_s=float(os.environ.get("JEGAL_CPU_BUDGET_S", 10.0)))
+        line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                **{k: v for k, v in c.items() if k not in ("value", "seconds")}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU top-k exchange: fused NVLink peer-memory kernels (p2p) or NCCL all-gather + merge")
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="the timed region runs max(--steps, enough steps for this many seconds): sustained clocks at every N")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-kernel stage table of the default line")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS["cfg5"]
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -372,7 +562,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        main_ours(args, wl, rank, local_rank, world)
+        if args.workload == "cfg5":
+            main_ours(args, wl, rank, local_rank, world)
+        else:
+            main_workload(args, rank, local_rank, world)
     finally:
         if world > 1 and dist.is_initialized():
             dist.destroy_process_group()

@@ -49,10 +49,11 @@ namespace {
 constexpr int kGThreads = 256;
 constexpr int kGThreadsFuse = 512;                // + 8 row-norm warps, one per k-block
 constexpr int kNormWarp0 = 8;
+constexpr int kNormTables = 2;                    // tile parity
 constexpr int kNormRows = 192;                    // per accumulator buffer: 128 frame slots + 64 word slots
 constexpr int kGStages = 32;                     // barrier slots; smem is a BYTE ring (see RingAlloc)
 constexpr int kNMax = 64;                        // words per clip on the N side
-constexpr uint32_t kGRingBytes = 216 * 1024;     // operand ring: a stage takes only the bytes it loads
+constexpr uint32_t kGRingBytes = 208 * 1024;     // operand ring: a stage takes only the bytes it loads
 constexpr int kNumAcc = 4;
 constexpr uint32_t kGTmemCols = kNumAcc * kNMax;  // 256
 constexpr int kBoxG = 32, kBoxC = 16;
@@ -217,13 +218,15 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   float* epi_f0 = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
   int32_t* epi_i0 = reinterpret_cast<int32_t*>(epi_f0 + 2 * kScratchF);
   volatile uint32_t* need_smem = reinterpret_cast<volatile uint32_t*>(epi_i0 + 8);  // [kGStages], producer-private
-  // kFuse: sum of squares of the rows of the tile in accumulator buffer b: [b][0..127] frames, [b][128..191] words;
-  // inv_w: per epilogue warp, the 64 inverse word norms of the tile it is draining
-  float* ssq = reinterpret_cast<float*>(const_cast<uint32_t*>(need_smem) + kGStages);
-  float* inv_w = ssq + kNumAcc * kNormRows;
+  // kFuse: partial sums of squares of a tile's rows, one table per (tile parity, k-block): [tb][kb][0..127] frames,
+  // [tb][kb][128..191] words (plain stores: fp32 shared-memory atomics are a CAS loop, 14 % of the kernel's stall
+  // samples when the eight k-block warps added into one table); inv_w: per epilogue warp, the 64 inverse word
+  // norms of the tile it is draining
+  float* part = reinterpret_cast<float*>(const_cast<uint32_t*>(need_smem) + kGStages);
+  float* inv_w = part + kNormTables * kNumKBlocks * kNormRows;
   const uint32_t n_full0 = smem_u32(inv_w + 4 * kNMax);
-  auto n_full = [&](int b) { return n_full0 + 8u * b; };              // all 8 partial sums of a tile are in
-  auto z_full = [&](int b) { return n_full0 + 8u * (kNumAcc + b); };  // k-block 0's sums are stored (the others add)
+  auto n_full = [&](int b) { return n_full0 + 8u * b; };                   // all 8 partial tables of a tile are written
+  auto n_empty = [&](int b) { return n_full0 + 8u * (kNormTables + b); };  // the 4 epilogue warps have read them
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,8 +241,10 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
       mbar_init(t_full(b), 1);
       mbar_init(t_empty(b), 4);
       if constexpr (kFuse != 0) {
-        mbar_init(n_full(b), kNumKBlocks);
-        mbar_init(z_full(b), 1);
+        if (b < kNormTables) {
+          mbar_init(n_full(b), kNumKBlocks);
+          mbar_init(n_empty(b), 4);
+        }
       }
     }
     fence_mbar_init();
@@ -410,14 +415,23 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         if constexpr (kFuse != 0) {
           // cos[t, w] = (g_t . c_w) / (max(||g_t||, eps) max(||c_w||, eps)): the row-norm warps summed the squares of
           // the very bytes the MMAs consumed; 1 / max(sqrt(s), eps) = rsqrt(max(s, eps^2))
-          JEGAL_GTRACED(1, mbar_wait_lean(n_full(buf), (tile / kNumAcc) & 1u));
-          const float* sq = ssq + buf * kNormRows;
+          const uint32_t tb = tile % kNormTables;
+          JEGAL_GTRACED(1, mbar_wait_lean(n_full(tb), (tile / kNormTables) & 1u));
+          const float* pt_ = part + tb * (kNumKBlocks * kNormRows);
           const float eps2 = p.row_eps * p.row_eps;
-          const float ig = rsqrtf(fmaxf(sq[et], eps2));
+          float sf = 0.f, sw0 = 0.f, sw1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < kNumKBlocks; ++k) {
+            sf += pt_[k * kNormRows + et];
+            sw0 += pt_[k * kNormRows + 128 + lane];
+            sw1 += pt_[k * kNormRows + 160 + lane];
+          }
+          const float ig = rsqrtf(fmaxf(sf, eps2));
           float* iw = inv_w + q * kNMax;
-          iw[lane] = rsqrtf(fmaxf(sq[128 + lane], eps2));
-          if (it.n16 > 2) iw[32 + lane] = rsqrtf(fmaxf(sq[160 + lane], eps2));
+          iw[lane] = rsqrtf(fmaxf(sw0, eps2));
+          iw[32 + lane] = rsqrtf(fmaxf(sw1, eps2));
           __syncwarp();
+          if (lane == 0) mbar_arrive(n_empty(tb));  // every lane of this warp has read the partial tables
 #pragma unroll
           for (int g = 0; g < kNMax / 16; ++g) {
             if (g < it.n16) {
@@ -434,7 +448,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty(buf));  // also releases ssq[buf] to the row-norm warps (and orders inv_w reuse)
+        if (lane == 0) mbar_arrive(t_empty(buf));
 
         const int32_t t = rt * 128 + et;
         const bool valid = t < it.T;
@@ -650,37 +664,34 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           const uint32_t stage = tile * kNumKBlocks + static_cast<uint32_t>(kb);
           const uint32_t slot = stage % kGStages, phase = (stage / kGStages) & 1u;
           const uint32_t a0 = base + my_off;
-          const uint32_t buf = tile % kNumAcc;
-          float* dst = ssq + buf * kNormRows;
-          // k-block 0 STORES its sums once the epilogue is done with the table's previous tile (no zeroing pass),
-          // the other seven add theirs behind it.  Four tiles of slack: these waits are almost never taken.
-          if (kb == 0) JEGAL_GTRACED(1, mbar_wait_lean(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u));
-          else JEGAL_GTRACED(1, mbar_wait_lean(z_full(buf), (tile / kNumAcc) & 1u));
+          const uint32_t tb = tile % kNormTables;
+          float* dst = part + (tb * kNumKBlocks + kb) * kNormRows;
+          // this warp's table of the tile two tiles back has been read by all four epilogue warps
+          JEGAL_GTRACED(1, mbar_wait_lean(n_empty(tb), ((tile / kNormTables) & 1u) ^ 1u));
           JEGAL_GTRACED(0, mbar_wait_lean(full(slot), phase));
           // a ROLLED loop over the stage's 16-row units (two in flight): the body is ~50 instructions and the
           // kernel's hot code has to fit the instruction cache
-          uint32_t au = a0;
+          // frame units that lie entirely past the clip's last frame (the box is rounded up to 32 rows) are skipped
+          const int32_t units_g = (rows + 15) >> 4;
+          const int32_t nwork = units_g + it.n16;
           float* d = dst + r16;
-          const float* d_words = dst + 128 + r16 - rows_g;
 #pragma unroll 2
-          for (int32_t u = 0; u < nunits; ++u, au += 2048u) {
+          for (int32_t u = 0; u < nwork; ++u) {
+            const bool is_word = u >= units_g;
+            const int32_t row0 = is_word ? rows_g + (u - units_g) * 16 : u * 16;  // first row of the unit in the stage
+            const uint32_t au = a0 + static_cast<uint32_t>(row0) * 128u;
             const uint4 x0 = lds128(au + lane_off[0]), x1 = lds128(au + lane_off[1]);
             const uint4 x2 = lds128(au + lane_off[2]), x3 = lds128(au + lane_off[3]);
             const float s0 = sumsq8<kBf16, kImpl>(x0, 0.f), s1 = sumsq8<kBf16, kImpl>(x1, 0.f);
             const float s2 = sumsq8<kBf16, kImpl>(x2, 0.f), s3 = sumsq8<kBf16, kImpl>(x3, 0.f);
             float ss = (s0 + s1) + (s2 + s3);
             ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-            float* dd = const_cast<float*>(u * 16 < rows_g ? d + u * 16 : d_words + u * 16);
-            if (lane < 16) {
-              if (kb == 0) *dd = ss;
-              else atomicAdd(dd, ss);
-            }
+            if (lane < 16) d[is_word ? 128 + (u - units_g) * 16 : row0] = ss;
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(empty(slot));
           if (lane == 0) {
-            if (kb == 0) mbar_arrive(z_full(buf));
-            mbar_arrive(n_full(buf));
+            mbar_arrive(empty(slot));
+            mbar_arrive(n_full(tb));
           }
         }
       }
@@ -706,7 +717,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
 constexpr size_t grouped_smem_bytes() {
   return 1024 + static_cast<size_t>(kGRingBytes) + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
          2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + sizeof(uint32_t) * kGStages + 16 +
-         sizeof(float) * (kNumAcc * kNormRows + 4 * kNMax) + 8 * 2 * kNumAcc;  // kFuse: squared row norms, inverse word norms, 2 x 4 barriers
+         sizeof(float) * (kNormTables * kNumKBlocks * kNormRows + 4 * kNMax) + 8 * 2 * kNormTables;  // kFuse: partial squared norms, inverse word norms, barriers
 }
 
 // one thread per group: softmax(scores / tau) within the group + first argmax

@@ -138,14 +138,20 @@ def prep(
 
 
 def clip_means(emb: torch.Tensor, layout: Layout, mean_eps: float = 1e-12, out_dtype: torch.dtype = torch.float32,
-               want_rows: bool = True, want_scale: bool = False):
+               want_rows: bool = True, want_scale: bool = False, out: Optional[torch.Tensor] = None):
     """K0 without the row output (read-only pass): per clip the unit-norm mean row ([n_clips, 512] in
     ``out_dtype``) and / or 1 / max(||mean||, mean_eps).  Returns (mean_rows | None, inv_meannorm | None)."""
     _check_rows(emb, layout, "clip_means")
     if emb.dtype not in _DT or out_dtype not in _DT:
         raise JegalError("clip_means: unsupported dtype")
     ctx = layout.ctx
-    rows = torch.empty((layout.n_clips, 512), dtype=out_dtype, device=emb.device) if want_rows else None
+    rows = None
+    if out is not None:
+        if tuple(out.shape) != (layout.n_clips, 512) or out.dtype not in _DT or not out.is_contiguous() or not out.is_cuda:
+            raise JegalError("clip_means: bad out tensor")
+        rows, out_dtype = out, out.dtype
+    elif want_rows:
+        rows = torch.empty((layout.n_clips, 512), dtype=out_dtype, device=emb.device)
     scale = torch.empty((layout.n_clips,), dtype=torch.float32, device=emb.device) if want_scale else None
     if rows is None and scale is None:
         raise JegalError("clip_means: nothing requested")

@@ -183,3 +183,189 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
     if len(gallery.chunks) == 1:
         return vals[0], idxs[0]
     return ops.topk_merge(vals, idxs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Host-to-host spotting / active-speaker scoring: the clip set sits in page-locked host memory (a packed index,
+# jegal_b200.index), its rows stream to the device in clip-aligned chunks on a copy stream and K3 / K0-means run on
+# chunk i while chunk i + 1 is in flight.  With the normalisation fused into K3's operand load there is no other
+# pass over the rows: the step is the PCIe transfer plus the kernels' tail on the last chunk.
+class HostClips:
+    """One side of a clip set: packed rows in page-locked host memory + a persistent device buffer of the same size."""
+
+    def __init__(self, rows_host: torch.Tensor, lengths, device=None):
+        if rows_host.is_cuda or rows_host.dim() != 2 or rows_host.shape[1] != 512:
+            raise JegalError("HostClips: rows_host must be a host [rows, 512] tensor")
+        self.rows = rows_host if rows_host.is_pinned() else rows_host.pin_memory()
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+        self.cu = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
+        if int(self.cu[-1]) != self.rows.shape[0]:
+            raise JegalError("HostClips: lengths do not add up to the row count")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rows_dev = torch.empty(self.rows.shape, dtype=self.rows.dtype, device=self.dev)
+        self._layouts = {}
+
+    @classmethod
+    def from_index(cls, idx, device=None) -> "HostClips":
+        return cls(idx.pinned(), idx.lengths, device)
+
+    @property
+    def n(self) -> int:
+        return len(self.lengths)
+
+    @property
+    def nbytes(self) -> int:
+        return self.rows.numel() * self.rows.element_size()
+
+    def layout(self, lo: int, hi: int) -> ops.Layout:
+        key = (lo, hi)
+        if key not in self._layouts:  # layouts own device tables: built once per chunk boundary
+            self._layouts[key] = ops.Layout.from_lengths(self.lengths[lo:hi])
+        return self._layouts[key]
+
+    def chunk(self, lo: int, hi: int):
+        r0, r1 = int(self.cu[lo]), int(self.cu[hi])
+        return self.rows_dev[r0:r1], self.layout(lo, hi)
+
+
+def clip_chunks(sides, n_chunks: int):
+    """Clip ranges [lo, hi) that cut the clip set into ~equal BYTE shares over all `sides` (HostClips that list the
+    same clips); the first chunk is half size so that scoring starts early."""
+    n = sides[0].n
+    if n == 0:
+        return []
+    per_clip = sum(s.lengths * s.rows.element_size() for s in sides).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(per_clip)])
+    n_chunks = max(1, min(int(n_chunks), n))
+    targets = cum[-1] * (np.arange(1, n_chunks * 2) / (n_chunks * 2.0))
+    cuts = np.searchsorted(cum, targets)
+    cuts = np.unique(np.concatenate([[0], cuts[:1], cuts[1::2], [n]]))  # first cut at 1/(2 n_chunks), then every 1/n_chunks
+    return [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+def _copy_chunks(sides, chunks, copy_stream, main):
+    """Enqueue the H2D copies of every chunk (all sides) on `copy_stream`; one event per chunk."""
+    copy_stream.wait_stream(main)  # the device buffers may still be read by kernels of the previous call
+    events = []
+    with torch.cuda.stream(copy_stream):
+        for lo, hi in chunks:
+            for s in sides:
+                r0, r1 = int(s.cu[lo]), int(s.cu[hi])
+                if r1 > r0:
+                    s.rows_dev[r0:r1].copy_(s.rows[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            events.append(ev)
+    return events
+
+
+_copy_streams = {}
+
+
+def _copy_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=dev)
+    return _copy_streams[key]
+
+
+def spot_streamed(g: HostClips, c: HostClips, word_idx, windows=None, thresh: float = 0.5, temp: float = 0.07,
+                  normalize: bool = True, n_chunks: int = 8, want_heat: bool = False) -> dict:
+    """evaluate_spotting.py:59-90 for a clip set in pinned host memory: H2D of chunk i + 1 overlaps K3 on chunk i.
+    Returns HOST numpy arrays: pred_frame, pred_score, correct (if windows), heat (flat [sum T], if asked)."""
+    if g.n != c.n:
+        raise JegalError("spot_streamed: gesture and content sides must list the same clips")
+    if c.n and int(c.lengths.max()) > 64:
+        raise JegalError("spot_streamed: a clip has more than 64 words; use scoring.spot_batch for such sets")
+    dev = g.dev
+    main = torch.cuda.current_stream(dev)
+    chunks = clip_chunks([g, c], n_chunks)
+    wi = torch.as_tensor(np.asarray(word_idx, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+    lo_d = hi_d = None
+    if windows is not None:
+        lo_d = torch.as_tensor(np.asarray(windows[0], dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+        hi_d = torch.as_tensor(np.asarray(windows[1], dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+    events = _copy_chunks([g, c], chunks, _copy_stream(dev), main)
+    outs = []
+    fused = g.rows.dtype in (torch.float16, torch.bfloat16) and c.rows.dtype == g.rows.dtype
+    for (lo, hi), ev in zip(chunks, events):
+        main.wait_event(ev)
+        g_rows, gl = g.chunk(lo, hi)
+        c_rows, cl = c.chunk(lo, hi)
+        kn = normalize
+        if not fused:  # fp32 storage: one K0 pass (normalise + cast) per chunk
+            g_rows = ops.prep(g_rows, gl, normalize=normalize)[0]
+            c_rows = ops.prep(c_rows, cl, normalize=normalize)[0]
+            kn = False
+        outs.append(ops.spot(g_rows, gl, c_rows, cl, wi[lo:hi], tau=temp, want_heat=want_heat,
+                             win_lo=None if lo_d is None else lo_d[lo:hi], win_hi=None if hi_d is None else hi_d[lo:hi],
+                             thresh=thresh, normalize=kn))
+    res = {}
+    for k in ("pred_frame", "pred_score", "correct", "heat"):
+        parts = [o[k] for o in outs if o[k] is not None]
+        res[k] = torch.cat(parts).cpu().numpy() if parts else None
+    if res["correct"] is not None:
+        res["correct"] = res["correct"].astype(bool)
+    return res
+
+
+def asd_streamed(g: HostClips, c: HostClips, pair_gest, pair_cont, tracks: int, prefixes=(2, 4, 6), temp: float = 0.07,
+                 mode: str = "reference", n_chunks: int = 8) -> dict:
+    """evaluate_asd.py:54-127 for clip sets in pinned host memory.  mode "reference": the clip means of chunk i
+    (one read-only pass, K0) are formed while chunk i + 1 is copied, then one warp per pair takes the cosine;
+    a pooling mode name: K4 (normalisation fused into the load) on the pairs of every gesture chunk, against the
+    content side, which is copied first.  Returns host arrays: scores [n_groups, tracks], pred {P: [n_groups]}."""
+    dev = g.dev
+    main = torch.cuda.current_stream(dev)
+    pg_h, pc_h = np.asarray(pair_gest, dtype=np.int32), np.asarray(pair_cont, dtype=np.int32)
+    pg = torch.as_tensor(pg_h).pin_memory().to(dev, non_blocking=True)
+    pc = torch.as_tensor(pc_h).pin_memory().to(dev, non_blocking=True)
+    cs = _copy_stream(dev)
+    c_chunks = clip_chunks([c], max(1, n_chunks // 4))
+    g_chunks = clip_chunks([g], n_chunks)
+    cs.wait_stream(main)
+    ev_c = _copy_chunks([c], c_chunks, cs, main)
+    ev_g = _copy_chunks([g], g_chunks, cs, main)
+    if mode == "reference":
+        gm = torch.empty((g.n, 512), dtype=torch.float32, device=dev)
+        cm = torch.empty((c.n, 512), dtype=torch.float32, device=dev)
+        for side, chunks, events, out in ((c, c_chunks, ev_c, cm), (g, g_chunks, ev_g, gm)):
+            for (lo, hi), ev in zip(chunks, events):
+                main.wait_event(ev)
+                rows, lay = side.chunk(lo, hi)
+                ops.clip_means(rows, lay, mean_eps=1e-8, out=out[lo:hi])
+        scores = ops.pair_cosine(gm, cm, pg, pc, normalize=False)
+    else:
+        if c.n and int(c.lengths.max()) > 64:
+            raise JegalError("asd_streamed: a content clip has more than 64 words; use scoring.asd_batch")
+        if g.rows.dtype not in (torch.float16, torch.bfloat16) or c.rows.dtype != g.rows.dtype:
+            raise JegalError("asd_streamed: pooling modes take 16-bit stored rows (same type on both sides)")
+        for ev in ev_c:
+            main.wait_event(ev)
+        c_rows, cl = c.chunk(0, c.n)
+        scores = torch.empty((pg_h.size,), dtype=torch.float32, device=dev)
+        order = np.argsort(pg_h, kind="stable")
+        bounds = np.searchsorted(pg_h[order], [lo for lo, _ in g_chunks] + [g.n])
+        for k, ((lo, hi), ev) in enumerate(zip(g_chunks, ev_g)):
+            main.wait_event(ev)
+            sel = order[bounds[k]:bounds[k + 1]]
+            if sel.size == 0:
+                continue
+            g_rows, gl = g.chunk(lo, hi)
+            contiguous = sel.size == sel[-1] - sel[0] + 1 and np.all(np.diff(sel) == 1)
+            sel_d = None if contiguous else torch.from_numpy(sel).to(dev)
+            pg_l = (pg[int(sel[0]):int(sel[-1]) + 1] if contiguous else pg[sel_d]) - lo
+            pc_l = pc[int(sel[0]):int(sel[-1]) + 1] if contiguous else pc[sel_d]
+            sc = ops.simpool_pairs(g_rows, gl, c_rows, cl, pg_l.contiguous(), pc_l.contiguous(), mode, normalize=True)["scores"]
+            if contiguous:
+                scores[int(sel[0]):int(sel[-1]) + 1] = sc
+            else:
+                scores[sel_d] = sc
+    n_groups = pg_h.size // tracks
+    pred = {}
+    for P in prefixes:
+        if P <= tracks:
+            pred[P] = ops.group_softmax(scores, n_groups, P, stride=tracks, tau=temp, want_probs=False)[1]
+    out = dict(scores=scores.cpu().numpy().reshape(n_groups, tracks), pred={P: v.cpu().numpy() for P, v in pred.items()})
+    out["acc"] = {P: (float((v == 0).mean()) if n_groups else float("nan")) for P, v in out["pred"].items()}
+    return out

@@ -184,3 +184,44 @@ def cfg5_gallery(n_query: int = 1000, n_gallery: int = 65536, T: int = 64, W: in
     rows = (torch.from_numpy(gt.astype(np.int64)).to(dev)[:, None] * W + word_of_frame[None, :]).reshape(-1)
     q += 1.0 * gal[rows]
     return _unit_rows(q), _unit_rows(gal), gt
+
+
+CFG5_BLOCK = 4096  # gallery clips per generator block
+
+
+def cfg5_sharded(n_query: int = 1000, n_gallery: int = 65536, T: int = 64, W: int = 16, seed: int = 1239, device="cpu",
+                 lo: int = 0, hi: Optional[int] = None, want_queries: bool = True):
+    """The planted large-gallery workload, generated so that ANY rank can materialise ANY clip range bit-identically:
+    the gallery is drawn in blocks of CFG5_BLOCK clips, block b from its own generator (seed, b), and the queries
+    (frames of query q echo the words of gallery clip gt[q], frame t speaks word t * W // T) from a third stream.
+    Returns (queries [n_query*T, 512] fp16 | None, gallery rows of clips [lo, hi) fp16, gt int32 [n_query]);
+    the shard of an N-GPU run is exactly rows [lo*W, hi*W) of the 1-GPU gallery."""
+    dev = torch.device(device)
+    hi = n_gallery if hi is None else hi
+    rng = np.random.default_rng(seed)
+    gt = rng.choice(n_gallery, size=n_query, replace=n_query > n_gallery).astype(np.int32)
+    shard = torch.empty((max(hi - lo, 0) * W, D), dtype=torch.float16, device=dev)
+    q = None
+    if want_queries:
+        gen_q = torch.Generator(device=device).manual_seed(seed * 1000003 + 999983)
+        q = torch.randn((n_query * T, D), generator=gen_q, device=dev)
+        word_of_frame = (torch.arange(T, device=dev) * W) // T
+    n_blocks = (n_gallery + CFG5_BLOCK - 1) // CFG5_BLOCK
+    for b in range(n_blocks):
+        b0, b1 = b * CFG5_BLOCK, min((b + 1) * CFG5_BLOCK, n_gallery)
+        in_shard = b0 < hi and b1 > lo
+        mine = np.nonzero((gt >= b0) & (gt < b1))[0] if want_queries else np.zeros(0, dtype=np.int64)
+        if not in_shard and mine.size == 0:
+            continue
+        gen = torch.Generator(device=device).manual_seed(seed * 1000003 + b)
+        blk = torch.randn(((b1 - b0) * W, D), generator=gen, device=dev)
+        if mine.size:
+            qi = torch.from_numpy(mine).to(dev)
+            rows = ((torch.from_numpy(gt[mine].astype(np.int64)).to(dev) - b0)[:, None] * W + word_of_frame[None, :])  # [m, T]
+            dst = (qi[:, None] * T + torch.arange(T, device=dev)[None, :]).reshape(-1)
+            q[dst] += blk[rows.reshape(-1)]
+        if in_shard:
+            s0, s1 = max(lo, b0), min(hi, b1)
+            shard[(s0 - lo) * W:(s1 - lo) * W] = _unit_rows(blk[(s0 - b0) * W:(s1 - b0) * W])
+        del blk
+    return (None if q is None else _unit_rows(q)), shard, gt

@@ -22,10 +22,23 @@ def main():
     parser.add_argument('--pool', type=str, default="reference",
                         choices=["reference", "mean_mean", "max_t_mean_w", "max_w_mean_t", "max_max"],
                         help="reference = cosine of mean-pooled clips (evaluate_retrieval.py:30-31,38-48)")
+    parser.add_argument('--index', type=str, default=None,
+                        help="Prefix of a packed clip index (jegal_b200.index); built from --path on first use")
     args = parser.parse_args()
-    d = pkl_io.load_dir(args.path)
-    print("No of files = ", len(d["files"]))
-    c2g, g2c = scoring.retrieval_metrics(d["gesture"], d["content"], mode=args.pool)
+    if args.index:
+        from jegal_b200 import index
+
+        ds = index.load_or_build(args.path, args.index)
+        print("No of files = ", ds.n)
+        if args.pool == "reference":  # the index keeps load_feats' temporal means (evaluate_retrieval.py:30-31)
+            g2c = scoring.compute_metrics(scoring.get_similarity_matrix(ds.gesture.mean, ds.content.mean))
+            c2g = scoring.compute_metrics(scoring.get_similarity_matrix(ds.content.mean, ds.gesture.mean))
+        else:
+            c2g, g2c = scoring.retrieval_metrics(ds.gesture.to_packed(), ds.content.to_packed(), mode=args.pool)
+    else:
+        d = pkl_io.load_dir(args.path)
+        print("No of files = ", len(d["files"]))
+        c2g, g2c = scoring.retrieval_metrics(d["gesture"], d["content"], mode=args.pool)
     print("Content to Gesture Retrieval scores:")
     scoring.print_computed_metrics(c2g)
     print("-" * 97)

@@ -30,3 +30,15 @@ def test_reference_arm_nonzero_rank_is_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_of_the_other_workloads():
+    """--workload cfg2|cfg3|cfg4 --impl reference: the reference-literal CPU legs of BASELINE.md 5.1 as oracle ports."""
+    env = dict(os.environ, JEGAL_CPU_BUDGET_S="0.5", JEGAL_CPU_SAMPLE_N="150")
+    for wl in ("cfg3", "cfg4"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", wl, "--steps", "1",
+                            "--warmup", "0"], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+        assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+        assert "evaluate_" in d["cpu_baseline"]["sample"] and d["scaling"] == "weak"

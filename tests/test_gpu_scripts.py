@@ -116,3 +116,47 @@ def test_plot_heatmap_script_and_index(pkl_dir, tmp_path):
     ref_s = oracle.get_similarity_matrix([oracle.mean_pool(g) for g in cs.gesture_list()],
                                          [oracle.mean_pool(c) for c in cs.content_list()]).numpy()
     assert np.abs(s[np.ix_(order, order)] - ref_s).max() < 2e-3
+
+
+def test_scripts_with_packed_index(pkl_dir, tmp_path):
+    """--index PREFIX: the first run builds the packed index from the .pkl directory, later runs read only the index
+    (rows streamed host->device overlapped with K3; retrieval / ASD from the stored temporal means) -- and print
+    exactly what the .pkl route prints."""
+    d, cs, names, csv = pkl_dir
+    prefix = str(tmp_path / "avs")
+    for script, extra in (("evaluate_spotting.py", []), ("evaluate_retrieval.py", []), ("evaluate_asd.py", ["--file", csv])):
+        plain = run(script, "--path", d, *extra)
+        built = run(script, "--path", d, "--index", prefix, *extra)
+        assert os.path.exists(prefix + ".meta.json") and os.path.exists(prefix + ".gesture.rows.npy")
+        again = run(script, "--path", "/nonexistent", "--index", prefix, *extra)  # the .pkl files are not needed any more
+        pick = lambda out: [l for l in out.splitlines() if l.startswith(("R@5", "Word Spotting", "2 spk", "4 spk", "6 spk"))]
+        assert pick(built) == pick(again) and len(pick(built)) >= 1
+        if script == "evaluate_spotting.py":  # same kernel, same operands: identical
+            assert pick(built) == pick(plain)
+        else:  # clip means from numpy (index) vs K0 (pkl route): equal up to summation order
+            for a, b in zip(pick(built), pick(plain)):
+                na, nb = [float(x) for x in __import__("re").findall(r"[-+]?\d+\.\d+", a)], [float(x) for x in __import__("re").findall(r"[-+]?\d+\.\d+", b)]
+                assert len(na) == len(nb) and all(abs(x - y) <= 2.5 for x, y in zip(na, nb)), (a, b)
+
+
+def test_streamed_spotting_and_asd_equal_resident(pkl_dir):
+    d, cs, names, _ = pkl_dir
+    from jegal_b200 import index, scoring, streaming
+    gi, ci = index.ClipIndex.from_clips(cs.gesture_list()), index.ClipIndex.from_clips(cs.content_list())
+    g, c = streaming.HostClips.from_index(gi), streaming.HostClips.from_index(ci)
+    tw = cs.target_word
+    st = np.array([cs.boundaries[i][int(tw[i])][1] for i in range(cs.n)])
+    en = np.array([cs.boundaries[i][int(tw[i])][2] for i in range(cs.n)])
+    win = (np.maximum(st - 9, 0), en + 9)
+    for n_chunks in (1, 3, 8):
+        r = streaming.spot_streamed(g, c, tw, windows=win, n_chunks=n_chunks, want_heat=True)
+        ref = scoring.spot_batch(cs.gesture_list(), cs.content_list(), tw, windows=win)
+        assert np.array_equal(r["pred_frame"], ref["pred_frame"]) and np.array_equal(r["correct"], ref["correct"])
+        assert np.array_equal(r["pred_score"], ref["pred_score"]) and np.array_equal(r["heat"], np.concatenate(ref["heat"]))
+    pair_g = np.arange(cs.n, dtype=np.int32)
+    pair_c = np.repeat(np.arange(0, cs.n, 6, dtype=np.int32), 6)
+    for mode in ("reference", "max_t_mean_w"):
+        ref = scoring.asd_batch(cs.content_list(), cs.gesture_list(), pair_g, pair_c, 6, mode=mode)
+        for n_chunks in (1, 5):
+            r = streaming.asd_streamed(g, c, pair_g, pair_c, 6, mode=mode, n_chunks=n_chunks)
+            assert np.array_equal(r["scores"], ref["scores"]) and all(np.array_equal(r["pred"][P], ref["pred"][P]) for P in (2, 4, 6))

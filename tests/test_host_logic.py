@@ -301,3 +301,45 @@ def test_streaming_chunk_schedule():
         if len(sch) >= 8:  # ramps up at the start, down at the end
             assert sch[0] <= sch[2] <= sch[3] and sch[-1] <= sch[-3] <= sch[-4]
     assert chunk_schedule(300, 64, ramp=False) == [64, 64, 64, 64, 44]
+
+
+def test_packed_index_round_trip(tmp_path):
+    """The packed clip index (rows as stored + offsets + numpy-semantics temporal means + the info fields the scripts
+    read) survives save / memory-mapped load, for both .pkl info flavours."""
+    import pandas as pd
+    from jegal_b200 import index, pkl_io
+    rng = np.random.default_rng(3)
+    d = tmp_path / "pkls"
+    d.mkdir()
+    clips = []
+    for i in range(7):
+        g = rng.standard_normal((int(rng.integers(3, 30)), 512)).astype(np.float16)
+        c = rng.standard_normal((int(rng.integers(1, 9)), 512)).astype(np.float16)
+        wb = [[f"w{k}", 2 * k, 2 * k + 1] for k in range(len(c))]
+        info = pd.Series({"phrase": "p", "word_boundaries": str(wb), "target_word_boundary": str(wb[0]), "filename": f"v{i}/00001"}) \
+            if i % 2 == 0 else {"fname": f"v{i}", "word_boundaries": wb, "text": "t"}
+        pkl_io.write_pkl(str(d / f"v{i}__00001.pkl"), g, c, info)
+        clips.append((g, c))
+    stats = index.build_from_pkl_dir(str(d), str(tmp_path / "idx"))
+    assert stats["n"] == 7 and stats["gesture_rows"] == sum(len(g) for g, _ in clips)
+    ds = index.load_or_build("/nonexistent", str(tmp_path / "idx"))
+    assert ds.n == 7 and ds.names == [f"v{i}__00001" for i in range(7)]
+    for i, (g, c) in enumerate(clips):
+        assert np.array_equal(np.asarray(ds.gesture.clip(i)), g) and np.array_equal(np.asarray(ds.content.clip(i)), c)
+        assert np.array_equal(ds.gesture.mean[i], g.mean(axis=0)) and ds.gesture.mean.dtype == np.float16
+        wb = ds.info[i]["word_boundaries"]
+        assert pkl_io.parse_boundaries(wb)[0][0] == "w0"
+    assert "target_word_boundary" in ds.info[0] and "text" in ds.info[1]
+
+
+def test_clip_chunks_cover_every_clip_once():
+    from types import SimpleNamespace
+    from jegal_b200.streaming import clip_chunks
+    rng = np.random.default_rng(5)
+    for n, k in [(1, 8), (5, 8), (100, 8), (20000, 8), (999, 3), (64, 1)]:
+        a = SimpleNamespace(n=n, lengths=rng.integers(1, 200, n).astype(np.int64), rows=SimpleNamespace(element_size=lambda: 2))
+        b = SimpleNamespace(n=n, lengths=rng.integers(1, 20, n).astype(np.int64), rows=SimpleNamespace(element_size=lambda: 2))
+        ch = clip_chunks([a, b], k)
+        assert ch[0][0] == 0 and ch[-1][1] == n and all(x[1] == y[0] for x, y in zip(ch[:-1], ch[1:]))
+        assert all(hi > lo for lo, hi in ch) and len(ch) <= k + 1
+    assert clip_chunks([SimpleNamespace(n=0, lengths=np.zeros(0, np.int64), rows=SimpleNamespace(element_size=lambda: 2))], 4) == []
