@@ -320,17 +320,31 @@ def main_ours(args, wl, rank, local_rank, world):
 
     # ---- end to end through the public host API: pinned host buffers in, top-k on the host out.
     # jegal_b200.streaming overlaps the H2D copy of gallery chunk i+1 with K0/K1/K2 on chunk i.
-    q_host = q_raw.cpu().pin_memory() if rank == 0 else None
-    gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), chunk_clips=max(2048, n_shard // 8),
-                                        device=dev, idx_base=lo)
-    h2d = gallery.nbytes + (Q * T * 512 * 2 if rank == 0 else 0)
+    # The query batch sits in a shared-memory segment of the host (the way a front-end process would hand it to the
+    # N scoring ranks): with N > 1 every rank copies 1/N of it over its own PCIe link and one NVLink all-gather
+    # replicates it (streaming.retrieve_topk_streamed, q_gather).
+    q_shared_path = None
+    if world > 1:
+        q_shared_path = f"/dev/shm/jegal_b200_queries_{os.environ.get('MASTER_PORT', '0')}.bin"
+        if rank == 0:
+            q_host = streaming.shared_host_tensor(q_shared_path, (Q * T, 512), torch.float16, create=True)
+            q_host.copy_(q_raw.cpu())
+        dist.barrier()
+        if rank != 0:
+            q_host = streaming.shared_host_tensor(q_shared_path, (Q * T, 512), torch.float16, create=False)
+    else:
+        q_host = q_raw.cpu().pin_memory()
+    # chunk sizes double (n/16, n/8, n/4, rest): scoring a chunk takes longer than copying the next one, so only the
+    # first copy is exposed and every further chunk would only add launch tails
+    gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), device=dev, idx_base=lo,
+                                        schedule=streaming.geometric_schedule(n_shard))
+    per_q = (Q * T + world - 1) // world
+    h2d = gallery.nbytes + max(0, min(Q * T, (rank + 1) * per_q) - rank * per_q) * 512 * 2
     d2h = Q * k * 8
 
     def e2e_step():
-        # queries start in rank 0's pinned host memory; they are copied (and with several GPUs broadcast) in 4
-        # parts, pipelined with the scoring of the first gallery chunk (jegal_b200.streaming)
-        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_parts=4,
-                                                  bcast_src=0 if world > 1 else None)
+        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_parts=1,
+                                                  q_gather=world > 1)
         if world > 1:
             vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
             idxs = torch.empty((world * Q, k), dtype=torch.int32, device=dev)
@@ -361,6 +375,13 @@ def main_ours(args, wl, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+        streaming.release_shared_host_tensor(q_host)
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(q_shared_path)
+            except OSError:
+                pass
     e2e_value = Q * G_total / float(te[0])
 
     if rank != 0:
@@ -405,7 +426,10 @@ def main_ours(args, wl, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(te[0]) * 1e3, "steps": e2e_steps,
-                "path": "pinned host fp16 embeddings -> chunked H2D (gallery chunks; with N > 1 also query parts, broadcast from rank 0) overlapped with K0/K1/K2 -> merge -> top-k (values, indices) -> host (jegal_b200.streaming.retrieve_topk_streamed)"},
+                "path": "page-locked host fp16 embeddings (gallery shard per rank; queries in one shared-memory segment) -> H2D: every "
+                        "rank copies its gallery chunks and 1/N of the queries, NVLink all-gather of the queries -> K0/K1/K2 per chunk "
+                        "overlapped with the next copy -> merge -> top-k (values, indices) -> host "
+                        "(jegal_b200.streaming.retrieve_topk_streamed)"},
         "gpu_launches": int(lc[0]),
         "roofline": {"bound": "tensor", "kernel": "simpool_kernel (K1)", "achieved": achieved, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],

@@ -41,11 +41,27 @@ def chunk_schedule(n_clips: int, chunk_clips: int, ramp: bool = True):
     return sched
 
 
+def geometric_schedule(n_clips: int, first_fraction: float = 1.0 / 16, min_clips: int = 128):
+    """Chunk sizes that double: n/16, n/8, n/4, rest.  When scoring a chunk takes longer than copying the next one
+    (config 5 at N >= 4: K1 needs ~2x the chunk's PCIe time) every copy after the first hides behind compute, so the
+    fewest chunks win: each launch has a tail and each chunk a handful of host-side calls."""
+    n = int(n_clips)
+    if n <= 0:
+        return []
+    sizes, c, left = [], max(min_clips, int(n * first_fraction)), n
+    while left > 0:
+        take = left if (left <= 2 * c or len(sizes) >= 3) else c
+        sizes.append(take)
+        left -= take
+        c *= 2
+    return sizes
+
+
 class StreamedGallery:
     """Pinned host gallery (packed fp16/fp32 rows + per-clip lengths) cut into clip-aligned chunks."""
 
     def __init__(self, rows_host: torch.Tensor, lengths: np.ndarray, chunk_clips: int = 8192, device=None,
-                 idx_base: int = 0, ramp: bool = True):
+                 idx_base: int = 0, ramp: bool = True, schedule=None):
         if rows_host.is_cuda or rows_host.dim() != 2 or rows_host.shape[1] != 512:
             raise JegalError("StreamedGallery: rows_host must be a host [rows, 512] tensor")
         self.rows = rows_host if rows_host.is_pinned() else rows_host.pin_memory()
@@ -55,7 +71,7 @@ class StreamedGallery:
         cu = np.concatenate([[0], np.cumsum(self.lengths)])
         self.chunks = []
         lo = 0
-        sched = chunk_schedule(len(self.lengths), chunk_clips, ramp)
+        sched = list(schedule) if schedule is not None else chunk_schedule(len(self.lengths), chunk_clips, ramp)
         if sum(sched) != len(self.lengths):
             raise JegalError(f"StreamedGallery: chunk schedule covers {sum(sched)} of {len(self.lengths)} clips")
         for size in sched:
@@ -73,6 +89,28 @@ class StreamedGallery:
     @property
     def nbytes(self) -> int:
         return self.rows.numel() * self.rows.element_size()
+
+
+def shared_host_tensor(path: str, shape, dtype: torch.dtype, create: bool) -> torch.Tensor:
+    """A host tensor backed by a shared-memory file (e.g. under /dev/shm) and registered with CUDA as page-locked:
+    every process of the box that maps the same path sees the same bytes and can start asynchronous H2D copies
+    from them.  The creator sizes the file; call ``release_shared_host_tensor`` before unlinking it."""
+    n = int(np.prod(shape))
+    item = torch.empty((), dtype=dtype).element_size()
+    if create:
+        with open(path, "wb") as f:
+            f.truncate(max(n * item, 1))
+    t = torch.from_file(path, shared=True, size=n, dtype=dtype).view(*shape)
+    if n and torch.cuda.is_available():
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n * item, 0)
+        if int(rc) != 0:
+            raise JegalError(f"cudaHostRegister({path}) failed with {int(rc)}")
+    return t
+
+
+def release_shared_host_tensor(t: torch.Tensor) -> None:
+    if t.numel() and torch.cuda.is_available():
+        torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
 
 
 def _query_parts(q_layout: ops.Layout, n_parts: int):
@@ -97,7 +135,7 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
                            mode: str = "max_t_mean_w", queries_are: str = "gesture",
                            q_dev: Optional[torch.Tensor] = None, q_parts: int = 1,
                            bcast_src: Optional[int] = None, group=None,
-                           q_dtype: torch.dtype = torch.float16) -> Tuple[torch.Tensor, torch.Tensor]:
+                           q_dtype: torch.dtype = torch.float16, q_gather: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery clips per query; queries and gallery start in (pinned) host memory.
     Returns DEVICE tensors (values [Q, k], global indices [Q, k]); call .cpu() to finish the round trip.
     ``q_dev`` may carry queries that are already on the device (e.g. after a broadcast).
@@ -106,16 +144,43 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
     is copied (and, with ``bcast_src`` set in a torch.distributed job, broadcast from that rank over NCCL)
     while part p is being scored against the first gallery chunk, so scoring starts after 1/q_parts of the
     query transfer instead of all of it.  On every rank but ``bcast_src`` ``q_host`` may be None (its dtype
-    is then ``q_dtype``)."""
+    is then ``q_dtype``).
+
+    ``q_gather`` (torch.distributed job, ``q_host`` visible to EVERY rank, e.g. ``shared_host_tensor``): the query
+    transfer is sharded like the gallery -- rank r copies rows r/N .. (r+1)/N of the queries over ITS OWN PCIe link and
+    one NCCL all-gather over NVLink replicates them, so the 65 MB query set costs every link 1/N of its copy time
+    instead of sitting in front of rank 0's gallery stream (1.2 ms of a 5.7 ms step at N = 8)."""
     dev = gallery.dev
     main = torch.cuda.current_stream(dev)
     nq = q_layout.n_clips
     import torch.distributed as dist
 
-    bcast = bcast_src is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    parts = _query_parts(q_layout, q_parts if q_dev is None else 1)
-    ready = [None] * len(parts)  # per part: a CUDA event (copy) or an NCCL work handle (broadcast)
-    if q_dev is None:
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    bcast = bcast_src is not None and multi
+    gather = q_gather and multi and q_dev is None
+    parts = _query_parts(q_layout, q_parts if (q_dev is None and not gather) else 1)
+    ready = [None] * len(parts)  # per part: a CUDA event (copy) or an NCCL work handle (broadcast / all-gather)
+    if gather:
+        if q_host is None:
+            raise JegalError("q_gather needs the queries in host memory every rank can read")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        rows = q_layout.rows
+        per = (rows + world - 1) // world
+        q_all = torch.empty((per * world, 512), dtype=q_host.dtype, device=dev)
+        mine = torch.empty((per, 512), dtype=q_host.dtype, device=dev)
+        r0 = min(rank * per, rows)
+        r1 = min(r0 + per, rows)
+        if not hasattr(gallery, "q_stream"):
+            gallery.q_stream = torch.cuda.Stream(device=dev)
+        gallery.q_stream.wait_stream(main)
+        with torch.cuda.stream(gallery.q_stream):
+            if r1 > r0:
+                mine[: r1 - r0].copy_(q_host[r0:r1], non_blocking=True)
+            ready[0] = dist.all_gather_into_tensor(q_all, mine, group=group, async_op=True)
+        q_all.record_stream(gallery.q_stream)
+        mine.record_stream(gallery.q_stream)
+        q_dev = q_all[:rows]
+    elif q_dev is None:
         i_am_src = (not bcast) or dist.get_rank(group) == bcast_src
         q_dtype = q_host.dtype if q_host is not None else q_dtype
         q_dev = torch.empty((q_layout.rows, 512), dtype=q_dtype, device=dev)
