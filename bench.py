@@ -334,10 +334,10 @@ def main_ours(args, wl, rank, local_rank, world):
             q_host = streaming.shared_host_tensor(q_shared_path, (Q * T, 512), torch.float16, create=False)
     else:
         q_host = q_raw.cpu().pin_memory()
-    # chunk sizes double (n/16, n/8, n/4, rest): scoring a chunk takes longer than copying the next one, so only the
-    # first copy is exposed and every further chunk would only add launch tails
+    # chunk sizes n x (1, 2, 5, 4, 2, 1, 1) / 16: whichever of copying and scoring is the bottleneck at this N, only
+    # 1/16 of the other is exposed at either end (streaming.balanced_schedule)
     gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), device=dev, idx_base=lo,
-                                        schedule=streaming.geometric_schedule(n_shard))
+                                        schedule=streaming.balanced_schedule(n_shard))
     per_q = (Q * T + world - 1) // world
     h2d = gallery.nbytes + max(0, min(Q * T, (rank + 1) * per_q) - rank * per_q) * 512 * 2
     d2h = Q * k * 8

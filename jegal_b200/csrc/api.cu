@@ -240,6 +240,7 @@ int64_t jegal_launch_count(const jegal_ctx* ctx) { return ctx ? ctx->launches : 
 
 int jegal_layout_create(jegal_ctx* ctx, const int32_t* cu_len_host, int32_t n_clips, void* stream_,
                         jegal_layout** out) {
+  JEGAL_NVTX("jegal_layout_create");
   if (!ctx || !out || !cu_len_host || n_clips < 0) return set_err(ctx, JEGAL_ERR_ARG, "layout_create: null/negative argument");
   *out = nullptr;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -301,6 +302,7 @@ int32_t jegal_layout_clips(const jegal_layout* L) { return L ? L->n_clips : 0; }
 int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype,
                int normalize_rows, float row_eps, float mean_eps, int out_dtype, void* out_rows_dev,
                float* inv_meannorm_dev, void* mean_rows_dev, void* stream) {
+  JEGAL_NVTX("jegal_prep (K0)");
   if (!ctx || !layout) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
   if (layout->n_clips == 0) return JEGAL_OK;
   if (!emb_dev || !out_rows_dev) return set_err(ctx, JEGAL_ERR_ARG, "prep: null argument");
@@ -312,6 +314,7 @@ int jegal_prep(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, 
 
 int jegal_clip_means(jegal_ctx* ctx, const jegal_layout* layout, const void* emb_dev, int in_dtype, float mean_eps,
                      int out_dtype, void* mean_rows_dev, float* inv_meannorm_dev, void* stream) {
+  JEGAL_NVTX("jegal_clip_means (K0 means)");
   if (!ctx || !layout) return set_err(ctx, JEGAL_ERR_ARG, "clip_means: null argument");
   if (layout->n_clips == 0) return JEGAL_OK;
   if (!emb_dev || (!mean_rows_dev && !inv_meannorm_dev)) return set_err(ctx, JEGAL_ERR_ARG, "clip_means: null argument");
@@ -326,6 +329,7 @@ int jegal_clip_means(jegal_ctx* ctx, const jegal_layout* layout, const void* emb
 int jegal_pair_cosine(jegal_ctx* ctx, const void* a_rows_dev, int64_t n_a, const void* b_rows_dev, int64_t n_b,
                       int dtype, const int32_t* pair_a_dev, const int32_t* pair_b_dev, int32_t n_pairs,
                       int normalize, float eps, float* scores_dev, void* stream) {
+  JEGAL_NVTX("jegal_pair_cosine");
   if (!ctx) return JEGAL_ERR_ARG;
   if (n_pairs < 0 || n_a < 0 || n_b < 0) return set_err(ctx, JEGAL_ERR_ARG, "pair_cosine: negative size");
   if (n_pairs == 0) return JEGAL_OK;
@@ -343,6 +347,7 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
                            const jegal_layout* cont_layout, const void* cont_rows_dev, int op_dtype,
                            int pool_mode, const float* gscale_dev, const float* cscale_dev,
                            float* scores_dev, int64_t ld_g, int64_t ld_c, void* stream_) {
+  JEGAL_NVTX("jegal_simpool_allpairs (K1)");
   if (!ctx || !gest_layout || !cont_layout) return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: null argument");
   if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16)
     return set_err(ctx, JEGAL_ERR_ARG, "simpool_allpairs: op_dtype must be JEGAL_BF16 or JEGAL_F16");
@@ -523,6 +528,7 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
 
 int jegal_topk(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
                int32_t idx_offset, float* topk_val_dev, int32_t* topk_idx_dev, void* stream) {
+  JEGAL_NVTX("jegal_topk (K2)");
   if (!ctx || (!scores_dev && n_g > 0 && n_q > 0) || !topk_val_dev || !topk_idx_dev)
     return set_err(ctx, JEGAL_ERR_ARG, "topk: null argument");
   if (k < 1 || k > 32) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "topk: k must be in [1, 32]");
@@ -533,6 +539,7 @@ int jegal_topk(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g
 
 int jegal_topk_merge(jegal_ctx* ctx, const float* vals_dev, const int32_t* idxs_dev, int32_t n_lists,
                      int32_t n_q, int32_t k, float* out_val_dev, int32_t* out_idx_dev, void* stream) {
+  JEGAL_NVTX("jegal_topk_merge (K2)");
   if (!ctx || !vals_dev || !idxs_dev || !out_val_dev || !out_idx_dev)
     return set_err(ctx, JEGAL_ERR_ARG, "topk_merge: null argument");
   if (k < 1 || k > 32) return set_err(ctx, JEGAL_ERR_UNSUPPORTED, "topk_merge: k must be in [1, 32]");
@@ -544,6 +551,7 @@ int jegal_topk_merge(jegal_ctx* ctx, const float* vals_dev, const int32_t* idxs_
 int jegal_rank_of_positive(jegal_ctx* ctx, const float* scores_dev, int32_t n_q, int32_t n_g,
                            int64_t ld_row, int64_t ld_col, const int32_t* gt_dev, int32_t* n_greater_dev,
                            int32_t* n_equal_dev, void* stream) {
+  JEGAL_NVTX("jegal_rank_of_positive (K2)");
   if (!ctx || !scores_dev || !n_greater_dev) return set_err(ctx, JEGAL_ERR_ARG, "rank_of_positive: null argument");
   if (n_q < 0 || n_g < 0) return set_err(ctx, JEGAL_ERR_ARG, "rank_of_positive: bad shape");
   if (!gt_dev && n_q > n_g) return set_err(ctx, JEGAL_ERR_ARG, "rank_of_positive: diagonal needs n_q <= n_g");

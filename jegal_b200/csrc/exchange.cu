@@ -281,6 +281,7 @@ void jegal_exchange_destroy(jegal_exchange* ex) {
 
 int jegal_topk_exchange(jegal_ctx* ctx, jegal_exchange* ex, const float* scores_dev, int32_t n_g, int64_t ld,
                         int32_t idx_offset, float* out_val_dev, int32_t* out_idx_dev, void* stream_) {
+  JEGAL_NVTX("jegal_topk_exchange (C1)");
   if (!ctx || !ex || !out_val_dev || !out_idx_dev || (!scores_dev && n_g > 0))
     return set_err(ctx, JEGAL_ERR_ARG, "topk_exchange: null argument");
   if (n_g < 0 || ld < n_g) return set_err(ctx, JEGAL_ERR_ARG, "topk_exchange: bad shape");

@@ -834,6 +834,7 @@ int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest
                const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
                const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh, uint8_t* correct_dev,
                void* stream_) {
+  JEGAL_NVTX("jegal_spot (K3)");
   if (!ctx || !gest_layout || !cont_layout || !gest_rows_dev || !cont_rows_dev || !word_idx_dev)
     return set_err(ctx, JEGAL_ERR_ARG, "spot: null argument");
   if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16) return set_err(ctx, JEGAL_ERR_ARG, "spot: bad op_dtype");
@@ -877,6 +878,7 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
                         const int32_t* pair_gest_dev, const int32_t* pair_cont_dev, int32_t n_pairs,
                         int32_t group_size, float tau, float* scores_dev, float* probs_dev,
                         int32_t* argmax_dev, void* stream_) {
+  JEGAL_NVTX("jegal_simpool_pairs (K4)");
   if (!ctx || !gest_layout || !cont_layout || !gest_rows_dev || !cont_rows_dev || !scores_dev)
     return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: null argument");
   if (op_dtype != JEGAL_BF16 && op_dtype != JEGAL_F16) return set_err(ctx, JEGAL_ERR_ARG, "simpool_pairs: bad op_dtype");
@@ -923,6 +925,7 @@ int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const v
 
 int jegal_group_softmax(jegal_ctx* ctx, const float* scores_dev, int32_t n_groups, int32_t group_size,
                         int64_t stride, float tau, float* probs_dev, int32_t* argmax_dev, void* stream_) {
+  JEGAL_NVTX("jegal_group_softmax");
   if (!ctx || !scores_dev) return set_err(ctx, JEGAL_ERR_ARG, "group_softmax: null argument");
   if (n_groups < 0 || group_size < 1 || stride < group_size || !(tau > 0.f))
     return set_err(ctx, JEGAL_ERR_ARG, "group_softmax: bad shape or tau");

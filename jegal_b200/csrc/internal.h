@@ -7,7 +7,19 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/jegal_b200.h"
+
+// NVTX range around the host side of a C-ABI entry point (header-only NVTX 3: a no-op unless a profiler
+// injects its library), so a timeline shows which call enqueued which kernels.
+struct JegalNvtxRange {
+  explicit JegalNvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~JegalNvtxRange() { nvtxRangePop(); }
+  JegalNvtxRange(const JegalNvtxRange&) = delete;
+  JegalNvtxRange& operator=(const JegalNvtxRange&) = delete;
+};
+#define JEGAL_NVTX(name) JegalNvtxRange jegal_nvtx_range__(name)
 
 namespace jegal {
 

@@ -130,6 +130,7 @@ extern "C" int jegal_segment_mean(jegal_ctx* ctx, const void* x_dev, int in_dtyp
                                   const int32_t* seg_begin_dev, const int32_t* seg_end_dev, int32_t n_seg,
                                   void* out_dev, int out_dtype, int64_t ld_out, int32_t col_off, void* stream) {
   using namespace jegal;
+  JEGAL_NVTX("jegal_segment_mean (K5)");
   if (!ctx) return JEGAL_ERR_ARG;
   if (n_seg < 0 || rows < 0) return set_err(ctx, JEGAL_ERR_ARG, "segment_mean: negative size");
   if (n_seg == 0) return JEGAL_OK;

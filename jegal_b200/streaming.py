@@ -41,20 +41,30 @@ def chunk_schedule(n_clips: int, chunk_clips: int, ramp: bool = True):
     return sched
 
 
-def geometric_schedule(n_clips: int, first_fraction: float = 1.0 / 16, min_clips: int = 128):
-    """Chunk sizes that double: n/16, n/8, n/4, rest.  When scoring a chunk takes longer than copying the next one
-    (config 5 at N >= 4: K1 needs ~2x the chunk's PCIe time) every copy after the first hides behind compute, so the
-    fewest chunks win: each launch has a tail and each chunk a handful of host-side calls."""
+def balanced_schedule(n_clips: int, min_clips: int = 128):
+    """Chunk sizes n x (1, 2, 5, 4, 2, 1, 1) / 16: small at BOTH ends, few chunks in between.  The host->device copies
+    run back to back on their own stream and chunk i is scored while chunk i + 1 arrives, so the step costs
+    copy(first chunk) + max(all copies, all scoring) + scoring(last chunk): whichever side is the bottleneck -- scoring
+    at N <= 2 (K1 needs 2x the gallery's PCIe time), the copies at N >= 4 on a host whose eight links share
+    ~236 GB/s (profiles/h2d_ceiling_r02.json: 23 - 36 GB/s per GPU with all eight active) -- only 1/16 of the other
+    side is exposed.  Every further chunk would add a launch tail and a handful of host-side calls."""
     n = int(n_clips)
     if n <= 0:
         return []
-    sizes, c, left = [], max(min_clips, int(n * first_fraction)), n
-    while left > 0:
-        take = left if (left <= 2 * c or len(sizes) >= 3) else c
-        sizes.append(take)
-        left -= take
-        c *= 2
-    return sizes
+    if n < 16 * min_clips:
+        return [n]
+    sizes = [(n * f) // 16 for f in (1, 2, 5, 4, 2, 1, 1)]
+    sizes[2] += n - sum(sizes)  # rounding goes to the largest chunk
+    out = []
+    for sz in sizes:  # merge chunks below min_clips into their predecessor (tiny galleries)
+        if sz <= 0:
+            continue
+        if out and (sz < min_clips or out[-1] < min_clips):
+            out[-1] += sz
+        else:
+            out.append(sz)
+    assert sum(out) == n and min(out) > 0, (n, out)
+    return out
 
 
 class StreamedGallery:

@@ -9,6 +9,10 @@ What is pinned (reference file:line):
   retrieval.npz  get_similarity_matrix + compute_metrics   evaluation/evaluate_retrieval.py:38-65
   spotting.npz   get_attn_matrix + get_spotting_acc        evaluation/evaluate_spotting.py:39-90
   asd.npz        load_feats + get_similarity_cos + evaluate_asd   evaluation/evaluate_asd.py:26-127
+  simpool_tiles.npz  the frame x word COSINE TILES of clip pairs, produced by the reference's own
+                 get_similarity_matrix (evaluate_retrieval.py:38-48: F.normalize + matmul) applied to a clip's
+                 frame rows and word rows, and the four poolings of each tile taken with numpy.  This pins the
+                 max-pool modes (which the released code does not contain) down to the final amax / mean.
   wordlevel.npz  JEGAL.get_word_level_embs + get_audio_word_level_embs   models/jegal.py:131-252
                  (method sources extracted with ast and executed: the module downloads XLM-R at import)
 """
@@ -165,6 +169,35 @@ def golden_asd():
     print("asd: accuracies", acc)
 
 
+def golden_simpool_tiles():
+    """Every T x W tile = ref.get_similarity_matrix(frames of clip i, words of clip j): the reference's own
+    normalise + matmul, on per-frame / per-word rows instead of per-clip means.  The pooled scores are plain
+    numpy reductions of those reference-produced tiles."""
+    ref = import_ref("evaluate_retrieval", ["--path", "/nonexistent"])
+    rng = np.random.default_rng(21)
+    n = 10
+    lt = np.concatenate([rng.integers(25, 140, size=n - 2), [1, 300]])   # incl. a one-frame clip and a > 256-frame clip
+    lw = np.concatenate([rng.integers(4, 30, size=n - 2), [1, 70]])      # incl. a one-word clip and a > 64-word clip
+    cs = synth.make_clipset(lt, lw, seed=202, a=0.3, b=1.0, sigma=1.0)
+    g_list, c_list = cs.gesture_list(), cs.content_list()
+    tiles, off = [], [0]
+    pooled = {m: np.zeros((n, n), dtype=np.float32) for m in ("mean_mean", "max_t_mean_w", "max_w_mean_t", "max_max")}
+    for i in range(n):
+        for j in range(n):
+            t = ref.get_similarity_matrix(g_list[i], c_list[j]).numpy()  # (T_i, W_j) cosines, fp32
+            assert t.shape == (len(g_list[i]), len(c_list[j]))
+            tiles.append(t.reshape(-1))
+            off.append(off[-1] + t.size)
+            pooled["mean_mean"][i, j] = t.mean(dtype=np.float32)
+            pooled["max_t_mean_w"][i, j] = t.max(axis=0).mean(dtype=np.float32)
+            pooled["max_w_mean_t"][i, j] = t.max(axis=1).mean(dtype=np.float32)
+            pooled["max_max"][i, j] = t.max()
+    np.savez_compressed(os.path.join(OUT, "simpool_tiles.npz"), gest=cs.gest.numpy(), cont=cs.cont.numpy(), cu_t=cs.cu_t,
+                        cu_w=cs.cu_w, tiles=np.concatenate(tiles), tile_off=np.array(off, dtype=np.int64),
+                        **{"pooled_" + k: v for k, v in pooled.items()})
+    print("simpool_tiles:", n * n, "tiles,", off[-1], "cosines")
+
+
 def ref_methods(names):
     """models/jegal.py cannot be imported offline (AutoTokenizer.from_pretrained at :13-14), so the wanted
     methods are cut out of its source with ast and compiled as plain functions (self is unused by them);
@@ -252,6 +285,7 @@ if __name__ == "__main__":
     golden_retrieval()
     golden_spotting()
     golden_asd()
+    golden_simpool_tiles()
     golden_wordlevel()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

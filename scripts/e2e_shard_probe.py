@@ -44,7 +44,7 @@ def main():
         for name, kw in (("ramp(default)", dict(chunk_clips=max(2048, n_shard // 8))), ("4 chunks", dict(chunk_clips=n_shard // 4, ramp=False)),
                          ("geometric", dict(chunk_clips=-1))):
             if kw.get("chunk_clips") == -1:
-                gal = streaming.StreamedGallery(g_host, np.full(n_shard, W), device=dev, schedule=streaming.geometric_schedule(n_shard))
+                gal = streaming.StreamedGallery(g_host, np.full(n_shard, W), device=dev, schedule=streaming.balanced_schedule(n_shard))
             else:
                 gal = streaming.StreamedGallery(g_host, np.full(n_shard, W), device=dev, **kw)
             for qp in (1, 4):

@@ -803,3 +803,29 @@ def test_asd_reference_mode_launches_no_tile_kernel(dev, golden):
             if r["pred"][p][grp] != g["preds"][grp, pi]:
                 assert abs(cos[r["pred"][p][grp]] - cos[g["preds"][grp, pi]]) < 1e-3
         assert abs(r["acc"][p] - g["accuracy"][pi]) <= 1.0 / n_groups + 1e-9
+
+
+# ----------------------------------------------------------------------------- reference-produced T x W tiles
+@pytest.mark.parametrize("op_dtype,tol", [(torch.bfloat16, TOL), (torch.float16, 2e-4)])
+def test_simpool_tiles_golden(dev, golden, op_dtype, tol):
+    """All four pooling modes against poolings of tiles the reference's own get_similarity_matrix produced
+    (tests/golden/simpool_tiles.npz), incl. a one-frame / one-word clip, a > 256-frame and a > 64-word clip;
+    top-k of the pooled scores bit-exact against a stable argsort of the golden scores where gaps allow."""
+    from jegal_b200 import ops, scoring
+    g = golden("simpool_tiles")
+    gest, cont = split(g["gest"], g["cu_t"]), split(g["cont"], g["cu_w"])
+    for mode in oracle.POOL_MODES:
+        got = scoring.score_allpairs(gest, cont, mode, op_dtype=op_dtype)
+        ref = g["pooled_" + mode]
+        assert np.abs(got - ref).max() < tol, (mode, float(np.abs(got - ref).max()))
+        v, i = ops.topk(torch.from_numpy(got).to(dev), 3)
+        rv, ri = oracle.topk(ref, 3)
+        bad = [q for q in range(len(gest)) for j in range(3)
+               if i[q, j].item() != ri[q, j] and abs(ref[q, ri[q, j]] - ref[q, i[q, j].item()]) > 2 * tol]
+        assert not bad
+    # the grouped kernel on the diagonal pairs (normalisation fused into the load for the fp16 rows)
+    narrow = [k for k in range(len(gest)) if len(cont[k]) <= 64]
+    r = scoring.asd_batch([cont[k] for k in narrow], [gest[k] for k in narrow], np.arange(len(narrow)), np.arange(len(narrow)), 1,
+                          prefixes=(1,), mode="max_t_mean_w", op_dtype=None if op_dtype == torch.float16 else op_dtype)
+    want = np.array([g["pooled_max_t_mean_w"][k, k] for k in narrow])
+    assert np.abs(r["scores"].reshape(-1) - want).max() < (2e-5 if op_dtype == torch.float16 else TOL)

@@ -343,3 +343,13 @@ def test_clip_chunks_cover_every_clip_once():
         assert ch[0][0] == 0 and ch[-1][1] == n and all(x[1] == y[0] for x, y in zip(ch[:-1], ch[1:]))
         assert all(hi > lo for lo, hi in ch) and len(ch) <= k + 1
     assert clip_chunks([SimpleNamespace(n=0, lengths=np.zeros(0, np.int64), rows=SimpleNamespace(element_size=lambda: 2))], 4) == []
+
+
+def test_balanced_schedule_covers_every_clip():
+    from jegal_b200.streaming import balanced_schedule
+    rng = np.random.default_rng(11)
+    for n in [0, 1, 2, 127, 128, 300, 2047, 8192, 65536, 21846] + [int(x) for x in rng.integers(1, 300000, 200)]:
+        sch = balanced_schedule(n)
+        assert sum(sch) == n and all(x > 0 for x in sch) and len(sch) <= 7 and (n > 0 or sch == [])
+        if n >= 16 * 128:  # small at both ends
+            assert sch[0] <= n // 16 + 1 and sch[-1] <= n // 16 + 1

@@ -5,6 +5,7 @@ import ast
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import oracle
 from jegal_testutil import split
@@ -129,3 +130,23 @@ def test_wordlevel_oracle_equals_reference_methods(golden):
                                            word_boundaries=bounds)
     assert np.array_equal(torch.cat(wt_h).numpy(), g["word_text_f16"])
     assert np.array_equal(torch.cat(wa_h).numpy(), g["word_audio_f16"])
+
+
+def test_simpool_tiles_golden_pins_the_max_pool_modes(golden):
+    """tests/golden/simpool_tiles.npz holds T x W cosine tiles produced by the REFERENCE's get_similarity_matrix
+    (evaluate_retrieval.py:38-48) on per-frame / per-word rows, and numpy poolings of them: the oracle's tile and
+    all four pooling modes (three of which the released code does not contain) must reproduce them."""
+    g = golden("simpool_tiles")
+    gest, cont = split(g["gest"], g["cu_t"]), split(g["cont"], g["cu_w"])
+    n = len(gest)
+    off = g["tile_off"]
+    for i in range(n):
+        for j in range(n):
+            t = g["tiles"][off[i * n + j]:off[i * n + j + 1]].reshape(len(gest[i]), len(cont[j]))
+            mine = oracle.cos_tile(gest[i], cont[j]).numpy()
+            assert np.abs(mine - t).max() < 2e-6
+            for mode in oracle.POOL_MODES:
+                assert abs(oracle.pool_tile(torch.from_numpy(t), mode) - g["pooled_" + mode][i, j]) < 1e-6
+    for mode in oracle.POOL_MODES:  # the vectorised restatement the GPU tests compare against
+        assert np.abs(oracle.simpool_allpairs(gest, cont, mode) - g["pooled_" + mode]).max() < 5e-6
+        assert np.abs(oracle.simpool_allpairs_loop(gest, cont, mode) - g["pooled_" + mode]).max() < 5e-6
