@@ -451,6 +451,7 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
   // inside a phase; so phases of R are made as large as stays L2-resident while every cluster
   // re-streams them, and column tiles are fetched with evict_first so they do not displace R.
   p.c_policy = env_int("JEGAL_C_POLICY", 2);
+  p.r_policy = env_int("JEGAL_R_POLICY", 1);
   const int64_t chunk_bytes = static_cast<int64_t>(env_int("JEGAL_CHUNK_MB", 24)) << 20;
   p.chunk_rtiles = static_cast<int32_t>(std::max<int64_t>(1, chunk_bytes / (static_cast<int64_t>(width) * kD * 2)));
   p.n_rows_R = static_cast<int32_t>(LR->rows);

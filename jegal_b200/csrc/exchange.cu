@@ -21,6 +21,7 @@
 #include <new>
 
 #include "internal.h"
+#include "warplist.cuh"
 
 struct jegal_exchange {
   jegal_ctx* ctx = nullptr;
@@ -53,52 +54,9 @@ __host__ __device__ inline size_t ex_idxs_off(int parity, int world, int n_q, in
   return kHdrBytes + 2 * ex_list_elems(world, n_q, k) * 4 + parity * ex_list_elems(world, n_q, k) * 4;
 }
 
-__device__ __forceinline__ bool better(float av, int32_t ai, float bv, int32_t bi) {
-  return av > bv || (av == bv && ai < bi);
-}
+using namespace k2;
 
-struct WarpList {  // same structure as in topk.cu: a descending 32-entry list across the lanes of a warp
-  float v;
-  int32_t i;
-  __device__ __forceinline__ void init() {
-    v = -INFINITY;
-    i = 0x7fffffff;
-  }
-  __device__ __forceinline__ void insert(float cv, int32_t ci, int lane) {
-    const bool worse = better(cv, ci, v, i);
-    const uint32_t wm = __ballot_sync(0xffffffffu, worse);
-    const int pos = __ffs(wm) - 1;
-    const float upv = __shfl_up_sync(0xffffffffu, v, 1);
-    const int32_t upi = __shfl_up_sync(0xffffffffu, i, 1);
-    if (pos >= 0) {
-      if (lane > pos) {
-        v = upv;
-        i = upi;
-      } else if (lane == pos) {
-        v = cv;
-        i = ci;
-      }
-    }
-  }
-  __device__ __forceinline__ void offer(float cv, int32_t ci, bool valid, int k, int lane) {
-    float tv = __shfl_sync(0xffffffffu, v, k - 1);
-    int32_t ti = __shfl_sync(0xffffffffu, i, k - 1);
-    uint32_t m = __ballot_sync(0xffffffffu, valid && better(cv, ci, tv, ti));
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const float bv = __shfl_sync(0xffffffffu, cv, src);
-      const int32_t bi = __shfl_sync(0xffffffffu, ci, src);
-      if (better(bv, bi, tv, ti)) {
-        insert(bv, bi, lane);
-        tv = __shfl_sync(0xffffffffu, v, k - 1);
-        ti = __shfl_sync(0xffffffffu, i, k - 1);
-      }
-    }
-  }
-};
-
-constexpr int kXWarps = 4;
+constexpr int kXWarps = kTopkWarps;  // the row scan is K2's (warplist.cuh)
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -123,24 +81,8 @@ topk_exchange_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, 
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
   const int32_t n4 = vec_ok ? (n_g >> 2) : 0;
   const float4* row4 = reinterpret_cast<const float4*>(row);
-  for (int32_t base = warp * 32; base < n4; base += kXWarps * 32) {
-    const int32_t j4 = base + lane;
-    const bool valid = j4 < n4;
-    const float4 x = valid ? __ldg(row4 + j4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    const float tv = __shfl_sync(0xffffffffu, L.v, k - 1);
-    const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-    if (!__any_sync(0xffffffffu, valid && mx >= tv)) continue;
-    const int32_t j = j4 * 4;
-    L.offer(x.x, j + 0, valid, k, lane);
-    L.offer(x.y, j + 1, valid, k, lane);
-    L.offer(x.z, j + 2, valid, k, lane);
-    L.offer(x.w, j + 3, valid, k, lane);
-  }
-  for (int32_t base = n4 * 4 + warp * 32; base < n_g; base += kXWarps * 32) {
-    const int32_t j = base + lane;
-    const bool valid = j < n_g;
-    L.offer(valid ? __ldg(row + j) : 0.f, j, valid, k, lane);
-  }
+  scan_row4(L, row4, 0, n4, k, warp, lane);  // the same pipelined scan as K2
+  scan_row_tail(L, row, n4 * 4, n_g, k, warp, lane);
   sv[warp][lane] = L.v;
   si[warp][lane] = L.i;
   __syncthreads();

@@ -57,6 +57,7 @@ struct SimpoolParams {
   int64_t ld_c;
   uint32_t idesc;
   int32_t c_policy;  // L2 eviction hint for column-operand tiles: 0 normal, 1 evict_last, 2 evict_first
+  int32_t r_policy;  // the same for row-operand tiles (default 1)
   unsigned long long* trace;  // nullable debug buffer: 16 cycle counters per CTA (JEGAL_K1_TRACE=1)
   int32_t dense;  // 1: every clip on both sides is one row -> plain GEMM epilogue (no pooling)
 };

@@ -375,7 +375,8 @@ simpool_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      const uint64_t pol_R = policy_evict_last();    // R chunk is re-streamed by every unit
+      // R chunk is re-streamed by every unit (r_policy, same encoding as c_policy; default evict_last)
+      const uint64_t pol_R = p.r_policy == 1 ? policy_evict_last() : p.r_policy == 2 ? policy_evict_first() : policy_evict_normal();
       // a column tile is fetched once per phase of R by exactly one cluster: no reuse inside a phase,
       // so it must not displace the R chunk every cluster re-streams (c_policy: 0 normal, 1 last, 2 first)
       const uint64_t pol_C = p.c_policy == 1 ? policy_evict_last() : p.c_policy == 2 ? policy_evict_first() : policy_evict_normal();

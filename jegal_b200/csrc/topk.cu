@@ -9,74 +9,12 @@
 #include <cstdlib>
 
 #include "internal.h"
+#include "warplist.cuh"
 
 namespace jegal {
 namespace {
 
-constexpr int kTopkWarps = 4;
-
-__device__ __forceinline__ bool better(float av, int32_t ai, float bv, int32_t bi) {
-  return av > bv || (av == bv && ai < bi);
-}
-
-// A warp holds a descending list of 32 (value, index) items, one per lane.
-struct WarpList {
-  float v;
-  int32_t i;
-  __device__ __forceinline__ void init() {
-    v = -INFINITY;
-    i = 0x7fffffff;
-  }
-  // insert (cv, ci) — warp-uniform arguments — which must beat lane 31's item
-  __device__ __forceinline__ void insert(float cv, int32_t ci, int lane) {
-    const bool worse = better(cv, ci, v, i);
-    const uint32_t wm = __ballot_sync(0xffffffffu, worse);
-    const int pos = __ffs(wm) - 1;
-    const float upv = __shfl_up_sync(0xffffffffu, v, 1);
-    const int32_t upi = __shfl_up_sync(0xffffffffu, i, 1);
-    if (pos >= 0) {
-      if (lane > pos) {
-        v = upv;
-        i = upi;
-      } else if (lane == pos) {
-        v = cv;
-        i = ci;
-      }
-    }
-  }
-  // like offer(), with the current k-th item (tv, ti) cached by the caller: an empty vote costs one ballot
-  __device__ __forceinline__ void offer_cached(float cv, int32_t ci, bool valid, int k, int lane, float& tv, int32_t& ti) {
-    uint32_t m = __ballot_sync(0xffffffffu, valid && better(cv, ci, tv, ti));
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const float bv = __shfl_sync(0xffffffffu, cv, src);
-      const int32_t bi = __shfl_sync(0xffffffffu, ci, src);
-      if (better(bv, bi, tv, ti)) {
-        insert(bv, bi, lane);
-        tv = __shfl_sync(0xffffffffu, v, k - 1);
-        ti = __shfl_sync(0xffffffffu, i, k - 1);
-      }
-    }
-  }
-  // offer one candidate per lane; candidates that beat the current k-th item get inserted
-  __device__ __forceinline__ void offer(float cv, int32_t ci, bool valid, int k, int lane) {
-    float tv = __shfl_sync(0xffffffffu, v, k - 1);
-    int32_t ti = __shfl_sync(0xffffffffu, i, k - 1);
-    uint32_t m = __ballot_sync(0xffffffffu, valid && better(cv, ci, tv, ti));
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const float bv = __shfl_sync(0xffffffffu, cv, src);
-      const int32_t bi = __shfl_sync(0xffffffffu, ci, src);
-      if (better(bv, bi, tv, ti)) {
-        insert(bv, bi, lane);
-        tv = __shfl_sync(0xffffffffu, v, k - 1);
-        ti = __shfl_sync(0xffffffffu, i, k - 1);
-      }
-    }
-  }
-};
+using namespace k2;
 
 // A query row is cut into gridDim.y column slices (16-byte aligned); block (q, s) streams slice s of
 // row q.  With more than one slice the block's list goes to a workspace and the LAST block of the
@@ -102,55 +40,8 @@ topk_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld, int32_t k
   const int32_t lo4 = min(slice * per, n4_all);
   const int32_t n4 = min(lo4 + per, n4_all);  // this block streams float4 indices [lo4, n4)
   const float4* row4 = reinterpret_cast<const float4*>(row);
-  // kU independent 16-byte loads per lane per batch, and the NEXT batch is already in flight while
-  // this one is examined (software pipelining); a whole batch is skipped with one vote when nothing
-  // in it can enter the current top-k
-  constexpr int kU = 4;
-  constexpr int kStride = kTopkWarps * 32 * kU;
-  const float4 kNegInf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  float4 x[kU], nx[kU];
-  int32_t base = lo4 + warp * 32 * kU;
-#pragma unroll
-  for (int u = 0; u < kU; ++u) {
-    const int32_t j4 = base + u * 32 + lane;
-    nx[u] = j4 < n4 ? __ldg(row4 + j4) : kNegInf4;
-  }
-  for (; base < n4; base += kStride) {
-#pragma unroll
-    for (int u = 0; u < kU; ++u) x[u] = nx[u];
-    const int32_t nbase = base + kStride;
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int32_t j4 = nbase + u * 32 + lane;
-      nx[u] = j4 < n4 ? __ldg(row4 + j4) : kNegInf4;
-    }
-    float tv = __shfl_sync(0xffffffffu, L.v, k - 1);
-    int32_t ti = __shfl_sync(0xffffffffu, L.i, k - 1);
-    float mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < kU; ++u) mx = fmaxf(mx, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
-    if (!__any_sync(0xffffffffu, mx >= tv)) continue;  // >= : an equal value with a lower index still wins
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int32_t j4 = base + u * 32 + lane;
-      const bool valid = j4 < n4;
-      const int32_t j = j4 * 4;
-      const float um = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
-      if (!__any_sync(0xffffffffu, valid && um >= tv)) continue;
-      L.offer_cached(x[u].x, j + 0, valid, k, lane, tv, ti);
-      L.offer_cached(x[u].y, j + 1, valid, k, lane, tv, ti);
-      L.offer_cached(x[u].z, j + 2, valid, k, lane, tv, ti);
-      L.offer_cached(x[u].w, j + 3, valid, k, lane, tv, ti);
-    }
-  }
-  if (slice == n_slices - 1) {  // scalar tail of the row (and unaligned rows)
-    for (int32_t b2 = n4_all * 4 + warp * 32; b2 < n_g; b2 += kTopkWarps * 32) {
-      const int32_t j = b2 + lane;
-      const bool valid = j < n_g;
-      const float xv = valid ? __ldg(row + j) : 0.f;
-      L.offer(xv, j, valid, k, lane);
-    }
-  }
+  scan_row4(L, row4, lo4, n4, k, warp, lane);
+  if (slice == n_slices - 1) scan_row_tail(L, row, n4_all * 4, n_g, k, warp, lane);  // and unaligned rows
   sv[warp][lane] = L.v;
   si[warp][lane] = L.i;
   __syncthreads();
@@ -244,6 +135,50 @@ rank_kernel(const float* __restrict__ scores, int32_t n_g, int64_t ld_row, int64
   }
 }
 
+// The same counts for a matrix whose QUERY index is the contiguous one (x.t() of a row-major matrix: ld_row == 1):
+// a block takes 32 consecutive queries, lane = query, and its 8 warps walk the candidates j = warp, warp + 8, ...
+// so every load is one coalesced 128-byte line (rank_kernel would read with stride ld_col per lane).
+__global__ void __launch_bounds__(256)
+rank_kernel_qmajor(const float* __restrict__ scores, int32_t n_q, int32_t n_g, int64_t ld_col,
+                   const int32_t* __restrict__ gt, int32_t* __restrict__ n_greater, int32_t* __restrict__ n_equal) {
+  __shared__ int32_t sg[8][32], se[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  const bool ok = q < n_q;
+  const int32_t g = ok ? (gt ? __ldg(gt + q) : static_cast<int32_t>(q)) : 0;
+  const float pos = ok ? __ldg(scores + q + static_cast<int64_t>(g) * ld_col) : 0.f;
+  int32_t cg = 0, ce = 0;
+  int32_t j = warp;
+  for (; j + 24 < n_g; j += 32) {  // four independent loads in flight per lane
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = ok ? __ldg(scores + q + static_cast<int64_t>(j + 8 * u) * ld_col) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      cg += x[u] > pos;
+      ce += x[u] == pos;
+    }
+  }
+  for (; j < n_g; j += 8) {
+    const float x = ok ? __ldg(scores + q + static_cast<int64_t>(j) * ld_col) : 0.f;
+    cg += x > pos;
+    ce += x == pos;
+  }
+  sg[warp][lane] = cg;
+  se[warp][lane] = ce;
+  __syncthreads();
+  if (warp == 0 && ok) {
+    int32_t tg = 0, te = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      tg += sg[w][lane];
+      te += se[w][lane];
+    }
+    n_greater[q] = tg;
+    if (n_equal) n_equal[q] = te;
+  }
+}
+
 }  // namespace
 
 int launch_topk(jegal_ctx* ctx, const float* scores, int32_t n_q, int32_t n_g, int64_t ld, int32_t k,
@@ -298,8 +233,12 @@ int launch_rank_of_positive(jegal_ctx* ctx, const float* scores, int32_t n_q, in
                             int64_t ld_row, int64_t ld_col, const int32_t* gt, int32_t* n_greater,
                             int32_t* n_equal, cudaStream_t stream) {
   if (n_q <= 0) return JEGAL_OK;
-  rank_kernel<<<static_cast<unsigned>(n_q), 256, 0, stream>>>(scores, n_g, ld_row, ld_col, gt, n_greater,
-                                                             n_equal);
+  if (ld_row == 1 && ld_col != 1) {
+    rank_kernel_qmajor<<<static_cast<unsigned>((n_q + 31) / 32), 256, 0, stream>>>(scores, n_q, n_g, ld_col, gt, n_greater,
+                                                                                 n_equal);
+  } else {
+    rank_kernel<<<static_cast<unsigned>(n_q), 256, 0, stream>>>(scores, n_g, ld_row, ld_col, gt, n_greater, n_equal);
+  }
   JEGAL_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;
   return JEGAL_OK;

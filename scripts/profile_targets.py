@@ -10,12 +10,12 @@ import torch
 from jegal_b200 import ops, synth
 
 dev = torch.device("cuda:0")
-which = set((sys.argv[1] if len(sys.argv) > 1 else "k0,k1,k2,k3,k4,k5,k1cfg2").split(","))
+which = set((sys.argv[1] if len(sys.argv) > 1 else "k0,k1,k2,k3,k4,k5,k1cfg2,dense").split(","))
 reps = int(os.environ.get("PROFILE_REPS", 2))
 
 if which & {"k0", "k1", "k2"}:
     Q, G, T, W = 1000, 65536, 64, 16
-    q, g, _ = synth.cfg5_gallery(Q, G, T, W, seed=1239, device=dev)
+    q, g, _ = synth.cfg5_sharded(Q, G, T, W, seed=1239, device=dev)
     ql, gl = ops.Layout.from_lengths([T] * Q), ops.Layout.from_lengths([W] * G)
     for _ in range(reps):
         q16, _ = ops.prep(q, ql)
@@ -29,13 +29,16 @@ if which & {"k0", "k1", "k2"}:
 if "k3" in which:
     cs = synth.cfg3_spotting(20000, device=dev)
     gl, cl = ops.Layout(cs.cu_t), ops.Layout(cs.cu_w)
-    g16, _ = ops.prep(cs.gest, gl)
-    c16, _ = ops.prep(cs.cont, cl)
     wi = torch.from_numpy(cs.target_word).to(dev)
     lo = torch.zeros(cs.n, dtype=torch.int32, device=dev)
     hi = torch.full((cs.n,), 1000, dtype=torch.int32, device=dev)
-    for _ in range(reps):
+    for _ in range(reps):  # K3 on the stored fp16 rows: normalisation fused into the operand load (grouped_kernel<0, 1>)
+        ops.spot(cs.gest, gl, cs.cont, cl, wi, win_lo=lo, win_hi=hi, normalize=True)
+    g16, _ = ops.prep(cs.gest, gl, out_dtype=torch.float16)
+    c16, _ = ops.prep(cs.cont, cl, out_dtype=torch.float16)
+    for _ in range(reps):  # K3 on pre-normalised operands (grouped_kernel<0, 0>), the round-1 pipeline's second half
         ops.spot(g16, gl, c16, cl, wi, win_lo=lo, win_hi=hi)
+    del g16, c16
     if "k5" in which:  # word-level mean pooling at the same clip shapes: every word = mean of its frames (D = 256 fp16)
         import numpy as np
         feats = torch.randn(gl.rows, 256, device=dev).half()
@@ -48,11 +51,13 @@ if "k4" in which:
     ds = synth.cfg4_asd(10000, 4, device=dev)
     cs = ds.clips
     gl, cl = ops.Layout(cs.cu_t), ops.Layout(cs.cu_w)
-    g16, gs = ops.prep(cs.gest, gl, normalize=False, want_mean_scale=True, mean_eps=1e-8)
-    c16, cs_ = ops.prep(cs.cont, cl, normalize=False, want_mean_scale=True, mean_eps=1e-8)
     pg, pc = torch.from_numpy(ds.pair_gest).to(dev), torch.from_numpy(ds.pair_cont).to(dev)
-    for _ in range(reps):
-        ops.simpool_pairs(g16, gl, c16, cl, pg, pc, "mean_mean", gscale=gs, cscale=cs_, group_size=4)
+    for _ in range(reps):  # the reference's ASD score: clip means (read-only K0) x2 + one warp per pair
+        gm, _ = ops.clip_means(cs.gest, gl, mean_eps=1e-8)
+        cm, _ = ops.clip_means(cs.cont, cl, mean_eps=1e-8)
+        ops.pair_cosine(gm, cm, pg, pc, normalize=False)
+    for _ in range(reps):  # K4 on the stored rows, T x W tile pooled (grouped_kernel<1, 1>)
+        ops.simpool_pairs(cs.gest, gl, cs.cont, cl, pg, pc, "max_t_mean_w", group_size=4, normalize=True)
 if "k1cfg2" in which:
     cs = synth.cfg2_retrieval(1000, device=dev)
     gl, cl = ops.Layout(cs.cu_t), ops.Layout(cs.cu_w)
@@ -61,5 +66,11 @@ if "k1cfg2" in which:
     for mode in ("max_t_mean_w", "max_w_mean_t"):
         for _ in range(reps):
             ops.simpool_allpairs(g16, gl, c16, cl, mode)
+if "dense" in which:  # plain-GEMM epilogue: 65536 x 1000 clip-level cosine matrix
+    a = torch.nn.functional.normalize(torch.randn(65536, 512, device=dev), dim=-1).bfloat16()
+    b = torch.nn.functional.normalize(torch.randn(1000, 512, device=dev), dim=-1).bfloat16()
+    la, lb = ops.Layout.from_lengths([1] * 65536), ops.Layout.from_lengths([1] * 1000)
+    for _ in range(reps):
+        ops.simpool_allpairs(a, la, b, lb, "mean_mean")
 torch.cuda.synchronize()
 print("done")

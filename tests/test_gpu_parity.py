@@ -251,6 +251,16 @@ def test_rank_of_positive_bit_exact(dev):
             g, e = ops.rank_of_positive(m)
             rg, re_ = oracle.rank_counts(m.cpu().numpy())
             assert np.array_equal(g.cpu().numpy(), rg) and np.array_equal(e.cpu().numpy(), re_)
+    # rectangular, ground truth given, both memory orders (the transposed view takes the query-major kernel)
+    x = torch.randint(0, 9, (77, 1003), device=dev).float() + torch.randn(77, 1003, device=dev).round() * 0.5
+    gt = torch.randint(0, 1003, (77,), device=dev, dtype=torch.int32)
+    xt = x.t().contiguous().t()  # same values, query index contiguous
+    assert xt.stride() == (1, 77)
+    xh, gh = x.cpu().numpy(), gt.cpu().numpy().astype(np.int64)
+    pos = xh[np.arange(77), gh][:, None]
+    for m in (x, xt):
+        g, e = ops.rank_of_positive(m, gt)
+        assert np.array_equal(g.cpu().numpy(), (xh > pos).sum(1)) and np.array_equal(e.cpu().numpy(), (xh == pos).sum(1))
 
 
 def test_retrieve_topk_gap_aware(dev):
