@@ -188,6 +188,16 @@ int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest
                const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh,
                uint8_t* correct_dev, void* stream);
 
+/* K3 from a DENSE cosine matrix, for clips with more than 64 words (long transcripts): cos_dev is the
+ * [rows of gest_layout, rows of cont_layout] frame x word cosine matrix of a GROUP of clips (row stride ld; e.g.
+ * jegal_simpool_allpairs over one-row layouts of the packed, normalised frames and words), of which only the
+ * block-diagonal (clip i's frames x clip i's words) is read.  Same outputs and arithmetic as jegal_spot
+ * (evaluate_spotting.py:52-54,70-82); heat_dev is required. */
+int jegal_spot_dense(jegal_ctx* ctx, const float* cos_dev, int64_t ld, const jegal_layout* gest_layout,
+                     const jegal_layout* cont_layout, const int32_t* word_idx_dev, float tau, float* heat_dev,
+                     float* full_heat_dev, const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
+                     const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh, uint8_t* correct_dev, void* stream);
+
 /* K4 — grouped scoring (evaluation/evaluate_asd.py:43-51,94-100): n_pairs listed
  * (gesture clip, content clip) pairs in groups of `group_size` consecutive pairs.
  *   normalize_rows / row_eps: as in jegal_spot (row normalisation fused into the load)

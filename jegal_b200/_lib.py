@@ -43,6 +43,7 @@ SYMBOLS = [
     "jegal_segment_mean",
     "jegal_clip_means",
     "jegal_pair_cosine",
+    "jegal_spot_dense",
 ]
 
 F32, F16, BF16 = 0, 1, 2
@@ -120,6 +121,8 @@ def load() -> C.CDLL:
         lib.jegal_topk_exchange.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
     if hasattr(lib, "jegal_segment_mean"):
         lib.jegal_segment_mean.argtypes = [vp, vp, C.c_int, i64, i32, vp, vp, i32, vp, C.c_int, i64, i32, vp]
+    if hasattr(lib, "jegal_spot_dense"):
+        lib.jegal_spot_dense.argtypes = [vp, vp, i64, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp]
     if hasattr(lib, "jegal_clip_means"):
         lib.jegal_clip_means.argtypes = [vp, vp, vp, C.c_int, f32, C.c_int, vp, vp, vp]
     if hasattr(lib, "jegal_pair_cosine"):

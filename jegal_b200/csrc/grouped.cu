@@ -749,6 +749,73 @@ __global__ void group_softmax_kernel(const float* __restrict__ scores, int32_t n
   }
 }
 
+// ---- spotting from a dense cosine matrix (clips with more words than the grouped kernel's 64 columns).
+// cos is [rows of the gesture layout, rows of the content layout] (K1's plain-GEMM epilogue over the packed frames x
+// words of a group of clips); only the block-diagonal is read: one warp per frame row takes the softmax over its
+// clip's words, exactly the arithmetic of the K3 epilogue.
+__global__ void __launch_bounds__(256)
+spot_dense_rows_kernel(const float* __restrict__ cos, int64_t ld, const int4* __restrict__ rowinfo, int64_t rows,
+                       const int32_t* __restrict__ cu_W, const int32_t* __restrict__ word_idx, float inv_tau,
+                       float* __restrict__ heat, float* __restrict__ full, const int64_t* __restrict__ full_off) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int4 ri = __ldg(rowinfo + r);
+  const int32_t clip = ri.x, t = static_cast<int32_t>(r) - ri.y, T = ri.z - ri.y;
+  const int32_t c0 = __ldg(cu_W + clip), W = __ldg(cu_W + clip + 1) - c0;
+  const int32_t target = __ldg(word_idx + clip);
+  const float* x = cos + r * ld + c0;
+  float m = -INFINITY;
+  for (int32_t w = lane; w < W; w += 32) m = fmaxf(m, __ldg(x + w));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float den = 0.f;
+  for (int32_t w = lane; w < W; w += 32) den += __expf((__ldg(x + w) - m) * inv_tau);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const float inv_den = 1.0f / den;
+  float* fh = full ? full + __ldg(full_off + clip) : nullptr;
+  for (int32_t w = lane; w < W; w += 32) {
+    const float pr = __expf((__ldg(x + w) - m) * inv_tau) * inv_den;
+    if (fh) fh[static_cast<int64_t>(w) * T + t] = pr;
+    if (w == target) heat[r] = pr;
+  }
+}
+
+// one warp per clip: first maximum of the clip's heat-map row, window + threshold decision (evaluate_spotting.py:72-82)
+__global__ void __launch_bounds__(256)
+spot_dense_clips_kernel(const float* __restrict__ heat, const int32_t* __restrict__ cu_T, int32_t n_clips,
+                        int32_t* __restrict__ pred_frame, float* __restrict__ pred_score, const int32_t* __restrict__ win_lo,
+                        const int32_t* __restrict__ win_hi, float thresh, uint8_t* __restrict__ correct) {
+  const int lane = threadIdx.x & 31;
+  const int32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_clips) return;
+  const int32_t r0 = __ldg(cu_T + i), r1 = __ldg(cu_T + i + 1);
+  float bv = -1.0f;
+  int32_t bt = 0x7fffffff;
+  for (int32_t r = r0 + lane; r < r1; r += 32) {
+    const float v = __ldg(heat + r);
+    if (v > bv) {  // a lane sees its frames in increasing order: strict > keeps its first maximum
+      bv = v;
+      bt = r - r0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int32_t ot = __shfl_xor_sync(0xffffffffu, bt, o);
+    if (ov > bv || (ov == bv && ot < bt)) {
+      bv = ov;
+      bt = ot;
+    }
+  }
+  if (lane == 0) {
+    if (pred_frame) pred_frame[i] = bt;
+    if (pred_score) pred_score[i] = bv;
+    if (correct) correct[i] = (bt >= __ldg(win_lo + i) && bt <= __ldg(win_hi + i) && bv >= thresh) ? 1 : 0;
+  }
+}
+
 int make_grouped_maps(jegal_ctx* ctx, GroupedMaps* m, const void* gest_rows, int64_t gest_n, const void* cont_rows,
                       int64_t cont_n, int op_dtype) {
   for (int i = 0; i < 4; ++i) {
@@ -872,6 +939,35 @@ int jegal_spot(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest
   rc = make_grouped_maps(ctx, &maps, gest_rows_dev, gest_layout->rows, cont_rows_dev, cont_layout->rows, op_dtype);
   if (rc != JEGAL_OK) return rc;
   return launch_grouped_any<EPI_SPOT>(ctx, normalize_rows, op_dtype, maps, p, static_cast<cudaStream_t>(stream_));
+}
+
+int jegal_spot_dense(jegal_ctx* ctx, const float* cos_dev, int64_t ld, const jegal_layout* gest_layout,
+                     const jegal_layout* cont_layout, const int32_t* word_idx_dev, float tau, float* heat_dev,
+                     float* full_heat_dev, const int64_t* full_off_dev, int32_t* pred_frame_dev, float* pred_score_dev,
+                     const int32_t* win_lo_dev, const int32_t* win_hi_dev, float thresh, uint8_t* correct_dev, void* stream_) {
+  JEGAL_NVTX("jegal_spot_dense (K3 for clips of more than 64 words)");
+  if (!ctx || !gest_layout || !cont_layout) return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: null argument");
+  if (gest_layout->n_clips != cont_layout->n_clips)
+    return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: gesture and content layouts must hold the same clips");
+  if (gest_layout->n_clips == 0) return JEGAL_OK;
+  if (!cos_dev || !word_idx_dev || !heat_dev) return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: null argument");
+  if (ld < cont_layout->rows) return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: ld is smaller than the content rows");
+  if (!(tau > 0.f)) return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: tau must be > 0");
+  if (full_heat_dev && !full_off_dev) return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: full_heat needs full_off");
+  if (correct_dev && (!win_lo_dev || !win_hi_dev)) return set_err(ctx, JEGAL_ERR_ARG, "spot_dense: correct needs win_lo/win_hi");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t rows = gest_layout->rows;
+  spot_dense_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      cos_dev, ld, gest_layout->rowinfo_dev, rows, cont_layout->cu_dev, word_idx_dev, 1.0f / tau, heat_dev, full_heat_dev,
+      full_off_dev);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  spot_dense_clips_kernel<<<static_cast<unsigned>((gest_layout->n_clips + 7) / 8), 256, 0, stream>>>(
+      heat_dev, gest_layout->cu_dev, gest_layout->n_clips, pred_frame_dev, pred_score_dev, win_lo_dev, win_hi_dev, thresh,
+      correct_dev);
+  JEGAL_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return JEGAL_OK;
 }
 
 int jegal_simpool_pairs(jegal_ctx* ctx, const jegal_layout* gest_layout, const void* gest_rows_dev,

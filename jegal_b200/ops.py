@@ -322,6 +322,37 @@ def spot(
     return dict(heat=heat, full=full, full_off=full_off, pred_frame=pred_frame, pred_score=pred_score, correct=correct)
 
 
+def spot_dense(cos: torch.Tensor, gest_layout: Layout, cont_layout: Layout, word_idx: torch.Tensor, tau: float = 0.07,
+               want_full: bool = False, win_lo: Optional[torch.Tensor] = None, win_hi: Optional[torch.Tensor] = None,
+               thresh: float = 0.5) -> dict:
+    """K3's outputs from a dense [sum T, sum W] frame x word cosine matrix of a group of clips (only the block
+    diagonal is read): the route for clips with more than 64 words.  Same dict as ``spot``."""
+    if not cos.is_cuda or cos.dtype != torch.float32 or cos.dim() != 2 or cos.stride(1) != 1:
+        raise JegalError("spot_dense: expected a CUDA fp32 matrix with unit column stride")
+    if cos.shape[0] != gest_layout.rows or cos.shape[1] != cont_layout.rows:
+        raise JegalError("spot_dense: the matrix must be [gesture rows, content rows] of the two layouts")
+    ctx = gest_layout.ctx
+    n, dev = gest_layout.n_clips, cos.device
+    if word_idx.dtype != torch.int32 or word_idx.numel() != n or not word_idx.is_cuda:
+        raise JegalError("spot_dense: word_idx must be CUDA int32 [n_clips]")
+    heat = torch.empty((gest_layout.rows,), dtype=torch.float32, device=dev)
+    full = full_off = None
+    if want_full:
+        sizes = gest_layout.lengths.astype(np.int64) * cont_layout.lengths.astype(np.int64)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        full_off = torch.from_numpy(off).to(dev)
+        full = torch.empty((int(off[-1]),), dtype=torch.float32, device=dev)
+    pred_frame = torch.empty((n,), dtype=torch.int32, device=dev)
+    pred_score = torch.empty((n,), dtype=torch.float32, device=dev)
+    correct = torch.empty((n,), dtype=torch.uint8, device=dev) if win_lo is not None else None
+    rc = ctx.lib.jegal_spot_dense(ctx.h, _ptr(cos), cos.stride(0), gest_layout.h, cont_layout.h, _ptr(word_idx), float(tau),
+                                  _ptr(heat), _ptr(full), _ptr(full_off), _ptr(pred_frame), _ptr(pred_score), _ptr(win_lo),
+                                  _ptr(win_hi), float(thresh), _ptr(correct), _stream())
+    ctx.check(rc, "jegal_spot_dense")
+    return dict(heat=heat, full=full, full_off=full_off, pred_frame=pred_frame, pred_score=pred_score, correct=correct)
+
+
 def simpool_pairs(
     gest_rows: torch.Tensor,
     gest_layout: Layout,

@@ -338,14 +338,6 @@ def _parse_wb(wb):
     return ast.literal_eval(wb) if isinstance(wb, str) else wb
 
 
-def _norm16(rows: torch.Tensor, normalize: bool, op_dtype: Optional[torch.dtype]) -> torch.Tensor:
-    """Normalised 16-bit rows of ONE clip for the K1 routes (one K0 launch)."""
-    od = op_dtype or (rows.dtype if rows.dtype in _NATIVE16 else torch.bfloat16)
-    if not normalize and rows.dtype == od:
-        return rows
-    return ops.prep(rows, layout_for([rows.shape[0]]), normalize=normalize, out_dtype=od)[0]
-
-
 def spot_batch(gestures, contents, word_idx: Sequence[int], temp: float = TEMP, normalize: bool = True,
                windows: Optional[Tuple[Sequence[int], Sequence[int]]] = None, thresh: float = 0.5,
                want_full: bool = False, op_dtype: Optional[torch.dtype] = None, fuse: bool = True,
@@ -410,26 +402,50 @@ def spot_batch(gestures, contents, word_idx: Sequence[int], temp: float = TEMP, 
             off = r["full_off"].cpu().numpy()
             for k_, i in enumerate(narrow):
                 full_l[i] = full[off[k_]:off[k_ + 1]].reshape(int(lw[i]), int(lt[i]))
-    for i in wide:
-        # more words than the grouped kernel's 64 columns (a long transcript): the same arithmetic from K1's
-        # plain-GEMM epilogue (frames x words cosines), the per-frame softmax over words and K2's first argmax
-        T, W = int(lt[i]), int(lw[i])
-        g16 = _norm16(g.rows[cu_t[i]:cu_t[i + 1]], normalize, op_dtype)
-        c16 = _norm16(c.rows[cu_w[i]:cu_w[i + 1]], normalize, op_dtype if op_dtype is not None else g16.dtype)
-        if c16.dtype != g16.dtype:
-            g16 = _norm16(g.rows[cu_t[i]:cu_t[i + 1]], normalize, c16.dtype)
-        cos = ops.simpool_allpairs(g16, layout_for(np.ones(T, dtype=np.int32)),
-                                   c16, layout_for(np.ones(W, dtype=np.int32)), "mean_mean")
-        probs, _ = ops.group_softmax(cos.view(-1), T, W, tau=temp)  # [T, W]: softmax over words for each frame
-        row = probs[:, int(word_idx[i])].contiguous()
-        v, f = ops.topk(row.view(1, T), 1)
-        heat_l[i] = row.cpu().numpy()
-        pred_frame[i] = int(f[0, 0])
-        pred_score[i] = float(v[0, 0])
-        if correct is not None:
-            correct[i] = bool(lo_h[i] <= pred_frame[i] <= hi_h[i] and pred_score[i] >= thresh)
-        if want_full:
-            full_l[i] = probs.t().contiguous().cpu().numpy()
+    if len(wide):
+        # More words than the grouped kernel's 64 columns (long transcripts): the same arithmetic from K1's plain-GEMM
+        # epilogue over the packed frames x words of a GROUP of such clips (one launch; the cross-clip blocks are
+        # wasted tensor time, bounded by the group size), then the per-frame softmax over the clip's words + argmax
+        # + decision in two small kernels (ops.spot_dense).  One launch set per group, not per clip.
+        budget = 32 << 20  # floats of the group's dense cosine matrix (128 MB)
+        groups, cur, st_, sw_ = [], [], 0, 0
+        for i in wide:
+            T, W = int(lt[i]), int(lw[i])
+            if cur and (st_ + T) * (sw_ + W) > budget:
+                groups.append(cur)
+                cur, st_, sw_ = [], 0, 0
+            cur.append(int(i))
+            st_, sw_ = st_ + T, sw_ + W
+        groups.append(cur)
+        for grp in groups:
+            keep = np.zeros(n, dtype=bool)
+            keep[grp] = True
+            g_rows = g.rows[torch.from_numpy(np.repeat(keep, lt)).to(dev)]
+            c_rows = c.rows[torch.from_numpy(np.repeat(keep, lw)).to(dev)]
+            gl_w, cl_w = layout_for(lt[grp]), layout_for(lw[grp])
+            od = op_dtype or (g_rows.dtype if (g_rows.dtype in _NATIVE16 and c_rows.dtype == g_rows.dtype) else torch.bfloat16)
+            g16 = g_rows if (not normalize and g_rows.dtype == od) else ops.prep(g_rows, gl_w, normalize=normalize, out_dtype=od)[0]
+            c16 = c_rows if (not normalize and c_rows.dtype == od) else ops.prep(c_rows, cl_w, normalize=normalize, out_dtype=od)[0]
+            cos = ops.simpool_allpairs(g16, layout_for(np.ones(gl_w.rows, dtype=np.int32)),
+                                       c16, layout_for(np.ones(cl_w.rows, dtype=np.int32)), "mean_mean")
+            lo = hi = None
+            if windows is not None:
+                lo, hi = torch.as_tensor(lo_h[grp], device=dev), torch.as_tensor(hi_h[grp], device=dev)
+            r = ops.spot_dense(cos, gl_w, cl_w, torch.as_tensor(word_idx[grp], device=dev), tau=temp, want_full=want_full,
+                               win_lo=lo, win_hi=hi, thresh=thresh)
+            pred_frame[grp] = r["pred_frame"].cpu().numpy()
+            pred_score[grp] = r["pred_score"].cpu().numpy()
+            if correct is not None:
+                correct[grp] = r["correct"].cpu().numpy().astype(bool)
+            heat = r["heat"].cpu().numpy()
+            cu_g = gl_w.cu_len
+            if want_full:
+                full = r["full"].cpu().numpy()
+                off = r["full_off"].cpu().numpy()
+            for k_, i in enumerate(grp):
+                heat_l[i] = heat[cu_g[k_]:cu_g[k_ + 1]]
+                if want_full:
+                    full_l[i] = full[off[k_]:off[k_ + 1]].reshape(int(lw[i]), int(lt[i]))
     out = dict(heat=heat_l, pred_frame=pred_frame, pred_score=pred_score, correct=correct)
     if want_full:
         out["full"] = full_l
@@ -540,15 +556,22 @@ def _pair_scores(g: PackedClips, c: PackedClips, pg: torch.Tensor, pc: torch.Ten
         sel = torch.from_numpy(narrow).to(dev)
         pc_n = torch.from_numpy(remap[pc_h[narrow]].astype(np.int32)).to(dev)
         scores[sel] = _pair_scores(g, cn, pg[sel].contiguous(), pc_n, pool, op_dtype, fuse)
-    cu_t, cu_w = gl.cu_len, cl.cu_len
-    for p in wide:
-        gi, ci = int(pg_h[p]), int(pc_h[p])
-        g16 = _norm16(g.rows[cu_t[gi]:cu_t[gi + 1]], True, op_dtype)
-        c16 = _norm16(c.rows[cu_w[ci]:cu_w[ci + 1]], True, op_dtype if op_dtype is not None else g16.dtype)
-        if c16.dtype != g16.dtype:
-            g16 = _norm16(g.rows[cu_t[gi]:cu_t[gi + 1]], True, c16.dtype)
-        one = ops.simpool_allpairs(g16, layout_for([g16.shape[0]]), c16, layout_for([c16.shape[0]]), pool)
-        scores[p] = one[0, 0]
+    # pairs whose content clip has more than 64 words: ONE all-pairs K1 launch over the gesture clips and the wide
+    # content clips these pairs mention (K1 pools any clip lengths), then a gather of the listed entries
+    g_ids, g_inv = np.unique(pg_h[wide], return_inverse=True)
+    c_ids, c_inv = np.unique(pc_h[wide], return_inverse=True)
+    lt = gl.lengths
+    keep_g = np.zeros(gl.n_clips, dtype=bool)
+    keep_g[g_ids] = True
+    keep_c = np.zeros(cl.n_clips, dtype=bool)
+    keep_c[c_ids] = True
+    gw = PackedClips(g.rows[torch.from_numpy(np.repeat(keep_g, lt)).to(dev)], layout_for(lt[g_ids]))
+    cw = PackedClips(c.rows[torch.from_numpy(np.repeat(keep_c, cl.lengths)).to(dev)], layout_for(cl.lengths[c_ids]))
+    od = op_dtype or (gw.rows.dtype if (gw.rows.dtype in _NATIVE16 and cw.rows.dtype == gw.rows.dtype) else torch.bfloat16)
+    g16 = ops.prep(gw.rows, gw.layout, normalize=True, out_dtype=od)[0]
+    c16 = ops.prep(cw.rows, cw.layout, normalize=True, out_dtype=od)[0]
+    sw = ops.simpool_allpairs(g16, gw.layout, c16, cw.layout, pool)
+    scores[torch.from_numpy(wide).to(dev)] = sw[torch.from_numpy(g_inv).to(dev), torch.from_numpy(c_inv).to(dev)]
     return scores
 
 

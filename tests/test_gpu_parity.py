@@ -839,3 +839,34 @@ def test_simpool_tiles_golden(dev, golden, op_dtype, tol):
                           prefixes=(1,), mode="max_t_mean_w", op_dtype=None if op_dtype == torch.float16 else op_dtype)
     want = np.array([g["pooled_max_t_mean_w"][k, k] for k in narrow])
     assert np.abs(r["scores"].reshape(-1) - want).max() < (2e-5 if op_dtype == torch.float16 else TOL)
+
+
+def test_wide_clip_routes_are_batched(dev):
+    """Clips with more than 64 words go through ONE launch set per group (K0 x2 + K1 dense + two small kernels for
+    spotting; K0 x2 + one all-pairs K1 for pair scores), however many such clips there are."""
+    from jegal_b200 import ops, scoring
+    def run(n_wide):
+        shapes = [(60 + 7 * i, 66 + 5 * i) for i in range(n_wide)] + [(56, 8), (40, 12)]
+        gest = [rand_clips(1, T, T, 300 + i)[0] for i, (T, W) in enumerate(shapes)]
+        cont = [rand_clips(1, W, W, 400 + i)[0] for i, (T, W) in enumerate(shapes)]
+        tw = [W // 2 for _, W in shapes]
+        gp, cp = scoring.PackedClips.from_list(gest), scoring.PackedClips.from_list(cont)
+        scoring.spot_batch(gp, cp, tw, want_full=True)          # first call builds the cached layouts
+        l0 = ops.Context.get().launches
+        r = scoring.spot_batch(gp, cp, tw, want_full=True)
+        n_spot = ops.Context.get().launches - l0
+        for i in range(len(shapes)):
+            a = oracle.get_attn_matrix(gest[i], cont[i])
+            assert np.abs(r["full"][i] - a).max() < PROB_TOL and r["pred_frame"][i] == int(np.argmax(a[tw[i]]))
+        pg = np.arange(len(shapes), dtype=np.int32)
+        pc = np.roll(np.arange(len(shapes), dtype=np.int32), 1)
+        scoring.asd_batch(cp, gp, pg, pc, 1, prefixes=(1,), mode="max_t_mean_w")
+        l0 = ops.Context.get().launches
+        r2 = scoring.asd_batch(cp, gp, pg, pc, 1, prefixes=(1,), mode="max_t_mean_w")
+        n_pairs = ops.Context.get().launches - l0
+        want = np.array([oracle.simpool_allpairs([gest[a_]], [cont[b_]], "max_t_mean_w")[0, 0] for a_, b_ in zip(pg, pc)])
+        assert np.abs(r2["scores"].reshape(-1) - want).max() < TOL
+        return n_spot, n_pairs
+    a3, b3 = run(3)
+    a9, b9 = run(9)
+    assert a3 == a9 and b3 == b9 and a3 <= 8 and b3 <= 10, (a3, a9, b3, b9)
