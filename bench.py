@@ -338,13 +338,14 @@ def main_ours(args, wl, rank, local_rank, world):
     # 1/16 of the other is exposed at either end (streaming.balanced_schedule)
     gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), device=dev, idx_base=lo,
                                         schedule=streaming.balanced_schedule(n_shard))
+    qg = ops.QueryGather(Q * T) if world > 1 else None  # C2: fused K0 + NVLink all-gather of the query operand
     per_q = (Q * T + world - 1) // world
     h2d = gallery.nbytes + max(0, min(Q * T, (rank + 1) * per_q) - rank * per_q) * 512 * 2
     d2h = Q * k * 8
 
-    def e2e_step():
+    def e2e_step(timeline=None):
         vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_parts=1,
-                                                  q_gather=world > 1)
+                                                  q_gather=qg if qg is not None else False, timeline=timeline)
         if world > 1:
             vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)
             idxs = torch.empty((world * Q, k), dtype=torch.int32, device=dev)
@@ -370,6 +371,15 @@ def main_ours(args, wl, rank, local_rank, world):
             hv, hi_ = e2e_step()
         sync_all(world)
         e2e_dt = (time.perf_counter() - t0) / e2e_steps
+        if args.e2e_timeline:  # one more step with CUDA events at every stage boundary, printed per rank (stderr)
+            tl = {}
+            th0 = time.perf_counter()
+            e2e_step(tl)
+            host_ms = (time.perf_counter() - th0) * 1e3
+            torch.cuda.synchronize()
+            print(json.dumps({"rank": rank, "e2e_step_host_ms": round(host_ms, 3), "timeline_ms": streaming.timeline_ms(tl)}),
+                  file=sys.stderr, flush=True)
+            sync_all(world)
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     hb = torch.tensor([h2d], dtype=torch.int64, device=dev)
     if world > 1:
@@ -427,7 +437,8 @@ def main_ours(args, wl, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(te[0]) * 1e3, "steps": e2e_steps,
                 "path": "page-locked host fp16 embeddings (gallery shard per rank; queries in one shared-memory segment) -> H2D: every "
-                        "rank copies its gallery chunks and 1/N of the queries, NVLink all-gather of the queries -> K0/K1/K2 per chunk "
+                        "rank copies its gallery chunks and 1/N of the queries; C2 = K0 on the slice + NVLink stores into every rank's "
+                        "operand buffer (peer memory, one kernel) -> K0/K1/K2 per gallery chunk "
                         "overlapped with the next copy -> merge -> top-k (values, indices) -> host "
                         "(jegal_b200.streaming.retrieve_topk_streamed)"},
         "gpu_launches": int(lc[0]),
@@ -520,6 +531,15 @@ def main_workload(args, rank, local_rank, world):
             w.e2e_step()
         sync_all(world)
         e2e_dt = (time.perf_counter() - t0) / e2e_steps
+        if args.e2e_timeline:  # one more step with CUDA events at every stage boundary, printed per rank (stderr)
+            tl = {}
+            th0 = time.perf_counter()
+            e2e_step(tl)
+            host_ms = (time.perf_counter() - th0) * 1e3
+            torch.cuda.synchronize()
+            print(json.dumps({"rank": rank, "e2e_step_host_ms": round(host_ms, 3), "timeline_ms": streaming.timeline_ms(tl)}),
+                  file=sys.stderr, flush=True)
+            sync_all(world)
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -572,6 +592,7 @@ def main():
                     help="the timed region runs max(--steps, enough steps for this many seconds): sustained clocks at every N")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--e2e-timeline", action="store_true", help="print a per-rank CUDA-event timeline of one e2e step to stderr")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-kernel stage table of the default line")
     args = ap.parse_args()
     wl = WORKLOADS["cfg5"]

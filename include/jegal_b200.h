@@ -230,6 +230,21 @@ void jegal_exchange_destroy(jegal_exchange* ex);
 int jegal_topk_exchange(jegal_ctx* ctx, jegal_exchange* ex, const float* scores_dev, int32_t n_g, int64_t ld,
                         int32_t idx_offset, float* out_val_dev, int32_t* out_idx_dev, void* stream);
 
+/* C2 — normalise + cast + all-gather of the REPLICATED operand of a sharded run in one kernel, over NVLink peer
+ * memory (no reference counterpart).  Every rank creates a gather block for an operand of `rows` x 512 16-bit values,
+ * exchanges the 64-byte IPC handles like jegal_exchange and connects.  jegal_prep_gather then takes this rank's slice
+ * (rows [row0, row0 + n_rows) of the raw matrix, any rank-disjoint cover of [0, rows)), applies K0's row arithmetic
+ * (x / max(||x||, row_eps) in fp32, one rounding to out_dtype) and stores the result rows into EVERY rank's block;
+ * the stream continues (a small wait kernel) once all ranks' slices of this call have landed locally.
+ * *result_dev: the complete [rows, 512] operand in this rank's memory, valid until the call after next. */
+typedef struct jegal_qgather jegal_qgather;
+int jegal_qgather_create(jegal_ctx* ctx, int32_t rank, int32_t world, int64_t rows, jegal_qgather** out);
+int jegal_qgather_ipc_handle(const jegal_qgather* qg, void* handle_out_64B);
+int jegal_qgather_connect(jegal_qgather* qg, const void* all_handles);
+void jegal_qgather_destroy(jegal_qgather* qg);
+int jegal_prep_gather(jegal_ctx* ctx, jegal_qgather* qg, const void* emb_slice_dev, int in_dtype, int64_t row0,
+                      int32_t n_rows, int normalize_rows, float row_eps, int out_dtype, void** result_dev, void* stream);
+
 /* softmax(scores / tau) and first argmax inside groups: group g covers
  * scores[g * stride .. g * stride + group_size).  stride >= group_size lets a caller score
  * prefixes of a wider candidate list (evaluate_asd.py:94-100 scores the first 2, 4, 6).

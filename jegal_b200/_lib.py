@@ -44,6 +44,11 @@ SYMBOLS = [
     "jegal_clip_means",
     "jegal_pair_cosine",
     "jegal_spot_dense",
+    "jegal_qgather_create",
+    "jegal_qgather_ipc_handle",
+    "jegal_qgather_connect",
+    "jegal_qgather_destroy",
+    "jegal_prep_gather",
 ]
 
 F32, F16, BF16 = 0, 1, 2
@@ -121,6 +126,13 @@ def load() -> C.CDLL:
         lib.jegal_topk_exchange.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
     if hasattr(lib, "jegal_segment_mean"):
         lib.jegal_segment_mean.argtypes = [vp, vp, C.c_int, i64, i32, vp, vp, i32, vp, C.c_int, i64, i32, vp]
+    if hasattr(lib, "jegal_prep_gather"):
+        lib.jegal_qgather_create.argtypes = [vp, i32, i32, i64, C.POINTER(vp)]
+        lib.jegal_qgather_ipc_handle.argtypes = [vp, vp]
+        lib.jegal_qgather_connect.argtypes = [vp, vp]
+        lib.jegal_qgather_destroy.argtypes = [vp]
+        lib.jegal_qgather_destroy.restype = None
+        lib.jegal_prep_gather.argtypes = [vp, vp, vp, C.c_int, i64, i32, C.c_int, f32, C.c_int, C.POINTER(vp), vp]
     if hasattr(lib, "jegal_spot_dense"):
         lib.jegal_spot_dense.argtypes = [vp, vp, i64, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp]
     if hasattr(lib, "jegal_clip_means"):

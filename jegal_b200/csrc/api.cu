@@ -375,6 +375,9 @@ int jegal_simpool_allpairs(jegal_ctx* ctx, const jegal_layout* gest_layout, cons
     // either orientation is exact: put the longer clips on the column side (fewer, longer
     // in-register reductions; fewer cross-lane combines per tile)
     cols_are_gest = gest_layout->rows * static_cast<int64_t>(nC) >= cont_layout->rows * static_cast<int64_t>(nG);
+    // one-row clips on both sides (plain GEMM epilogue): the columns are the side whose index is contiguous in
+    // the output, so every epilogue thread owns a contiguous stretch of an output row (256-bit stores)
+    if (gest_layout->uniform_len == 1 && cont_layout->uniform_len == 1) cols_are_gest = ld_g == 1;
     const int force = env_int("JEGAL_SIMPOOL_COLS", -1);  // testing knob: 0 = content, 1 = gesture
     if (force >= 0) cols_are_gest = force != 0;
   }

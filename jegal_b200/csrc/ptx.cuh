@@ -310,6 +310,12 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
 __device__ __forceinline__ void st_global_cs_f32(float* addr, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
+// 256-bit streaming store (sm_100: STG.E.EF.256): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void st_global_cs_v8_f32(float* addr, const float (&v)[8]) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void red_global_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }

@@ -186,6 +186,18 @@ __device__ __forceinline__ void store_chunk_dense(const uint32_t (&v)[32], int32
   if (!(rc.flags & kRcValid)) return;
   float* dst = rc.out_row + static_cast<int64_t>(cclip) * p.ld_c;
   const float rs = rc.rscale;
+  if (p.ld_c == 1 && ncols >= 32 && !p.cscale && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0u) {
+    // a full chunk of this thread's output row, 32-byte aligned: four 256-bit stores, each one whole sector
+    // (16-byte stores filled a sector in two instructions: the epilogue was bound by LSU transactions, 31 % of HBM)
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[j + i]) * rs;
+      st_global_cs_v8_f32(dst + j, o);
+    }
+    return;
+  }
   if (p.ld_c == 1 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(p.cscale + cclip)) & 15u) == 0u) {
     // this thread's 32 cosines are contiguous in the output row: 16-byte stores (4x fewer store instructions)
 #pragma unroll

@@ -496,3 +496,72 @@ class TopkExchange:
                 self.h = None
         except Exception:
             pass
+
+
+class _DevArray:
+    """A device allocation owned by the library, exposed through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+class QueryGather:
+    """C2: normalise + cast + all-gather of the replicated (query-side) operand over NVLink peer memory, one kernel.
+
+    Construction is collective (every rank of ``group``): the CUDA IPC handles of the per-rank operand blocks are
+    all-gathered through torch.distributed and opened.  ``prep_gather(slice, row0)`` takes this rank's rows
+    [row0, row0 + len(slice)) of the raw [rows, 512] matrix and returns the complete normalised 16-bit operand
+    (a view of library-owned memory, valid until the call after next)."""
+
+    def __init__(self, rows: int, group=None, device: Optional[int] = None):
+        import torch.distributed as dist
+
+        self.ctx = Context.get(device)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rows = int(rows)
+        self.group = group
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.jegal_qgather_create(self.ctx.h, self.rank, self.world, self.rows, C.byref(h)), "jegal_qgather_create")
+        self.h = h
+        mine = (C.c_uint8 * 64)()
+        self.ctx.check(self.ctx.lib.jegal_qgather_ipc_handle(self.h, mine), "jegal_qgather_ipc_handle")
+        handles = [bytes(mine)]
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine), group=group)
+            handles = gathered
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.ctx.check(self.ctx.lib.jegal_qgather_connect(self.h, buf), "jegal_qgather_connect")
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def slice_rows(self):
+        """This rank's share [r0, r1) of the rows (equal ceil-sized slices)."""
+        per = (self.rows + self.world - 1) // self.world
+        r0 = min(self.rank * per, self.rows)
+        return r0, min(r0 + per, self.rows)
+
+    def prep_gather(self, emb_slice: torch.Tensor, row0: int, normalize: bool = True, row_eps: float = 1e-12,
+                    out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        if emb_slice.numel() and (not emb_slice.is_cuda or emb_slice.dim() != 2 or emb_slice.shape[1] != 512 or not emb_slice.is_contiguous()):
+            raise JegalError("prep_gather: expected a contiguous CUDA [n, 512] slice")
+        if emb_slice.dtype not in _DT or out_dtype not in (torch.bfloat16, torch.float16):
+            raise JegalError("prep_gather: unsupported dtype")
+        res = C.c_void_p()
+        rc = self.ctx.lib.jegal_prep_gather(self.ctx.h, self.h, _ptr(emb_slice) if emb_slice.numel() else C.c_void_p(0), _DT[emb_slice.dtype],
+                                            int(row0), int(emb_slice.shape[0]), int(bool(normalize)), float(row_eps), _DT[out_dtype],
+                                            C.byref(res), _stream())
+        self.ctx.check(rc, "jegal_prep_gather")
+        dev = torch.device("cuda", self.ctx.device)
+        t = torch.as_tensor(_DevArray(res.value, (self.rows, 512), "<i2"), device=dev)
+        return t.view(out_dtype)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.ctx.lib.jegal_qgather_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

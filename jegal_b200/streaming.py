@@ -89,11 +89,14 @@ class StreamedGallery:
             self.chunks.append((lo, hi, int(cu[lo]), int(cu[hi]), ops.Layout.from_lengths(self.lengths[lo:hi])))
             lo = hi
         max_rows = max((c[3] - c[2] for c in self.chunks), default=0)
-        self.stage = [torch.empty((max_rows, 512), dtype=self.rows.dtype, device=self.dev) for _ in range(2)]
+        # The raw rows land in a device buffer as large as the whole gallery (shard): no copy ever waits for the
+        # scoring of an earlier chunk to release a staging buffer, so the PCIe link runs back to back -- with two
+        # chunk-sized staging buffers the copies were throttled by the compute pipeline, and at N >= 4, where the
+        # host's shared H2D ceiling makes the copies the bottleneck, every such bubble lengthened the step.
+        self.stage = torch.empty((int(cu[-1]), 512), dtype=self.rows.dtype, device=self.dev)
         self.op16 = [torch.empty((max_rows, 512), dtype=torch.bfloat16, device=self.dev) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in self.chunks]
         self.n_clips = len(self.lengths)
 
     @property
@@ -145,7 +148,8 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
                            mode: str = "max_t_mean_w", queries_are: str = "gesture",
                            q_dev: Optional[torch.Tensor] = None, q_parts: int = 1,
                            bcast_src: Optional[int] = None, group=None,
-                           q_dtype: torch.dtype = torch.float16, q_gather: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                           q_dtype: torch.dtype = torch.float16, q_gather=False,
+                           timeline: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery clips per query; queries and gallery start in (pinned) host memory.
     Returns DEVICE tensors (values [Q, k], global indices [Q, k]); call .cpu() to finish the round trip.
     ``q_dev`` may carry queries that are already on the device (e.g. after a broadcast).
@@ -158,19 +162,51 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
 
     ``q_gather`` (torch.distributed job, ``q_host`` visible to EVERY rank, e.g. ``shared_host_tensor``): the query
     transfer is sharded like the gallery -- rank r copies rows r/N .. (r+1)/N of the queries over ITS OWN PCIe link and
-    one NCCL all-gather over NVLink replicates them, so the 65 MB query set costs every link 1/N of its copy time
-    instead of sitting in front of rank 0's gallery stream (1.2 ms of a 5.7 ms step at N = 8)."""
+    one all-gather over NVLink replicates them, so the 65 MB query set costs every link 1/N of its copy time
+    instead of sitting in front of rank 0's gallery stream (1.2 ms of a 5.7 ms step at N = 8).  ``q_gather=True``
+    uses an NCCL all-gather of the raw rows followed by K0 on every rank; passing an ``ops.QueryGather`` instead
+    fuses normalise + cast + all-gather into one kernel over peer memory (C2): each rank prepares only its slice
+    and stores the operand rows straight into every rank's buffer."""
     dev = gallery.dev
     main = torch.cuda.current_stream(dev)
     nq = q_layout.n_clips
     import torch.distributed as dist
 
+    def mark(name, stream=None):  # timeline: CUDA events, read by `timeline_ms` after the caller synchronised
+        if timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream or main)
+            timeline.setdefault("events", []).append((name, ev))
+
+    mark("start")
+
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     bcast = bcast_src is not None and multi
-    gather = q_gather and multi and q_dev is None
+    fused_gather = isinstance(q_gather, ops.QueryGather) and q_dev is None
+    gather = bool(q_gather) and multi and q_dev is None and not fused_gather
+    q_ready16 = None  # the prepared query operand when it does not come from K0 below
     parts = _query_parts(q_layout, q_parts if (q_dev is None and not gather) else 1)
     ready = [None] * len(parts)  # per part: a CUDA event (copy) or an NCCL work handle (broadcast / all-gather)
-    if gather:
+    if fused_gather:
+        if q_host is None:
+            raise JegalError("q_gather needs the queries in host memory every rank can read")
+        qg = q_gather
+        r0, r1 = qg.slice_rows()
+        mine = torch.empty((max(r1 - r0, 0), 512), dtype=q_host.dtype, device=dev)
+        if not hasattr(gallery, "q_stream"):
+            gallery.q_stream = torch.cuda.Stream(device=dev)
+        gallery.q_stream.wait_stream(main)
+        with torch.cuda.stream(gallery.q_stream):
+            if r1 > r0:
+                mine.copy_(q_host[r0:r1], non_blocking=True)
+            mark("query slice copied", gallery.q_stream)
+            q_ready16 = qg.prep_gather(mine, r0)  # K0 on the slice + NVLink stores to every rank + flag wait
+            ready[0] = torch.cuda.Event()
+            ready[0].record(gallery.q_stream)
+        mine.record_stream(gallery.q_stream)
+        parts = _query_parts(q_layout, 1)
+        q_dev = q_ready16  # (only its shape matters below)
+    elif gather:
         if q_host is None:
             raise JegalError("q_gather needs the queries in host memory every rank can read")
         world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -186,6 +222,7 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
         with torch.cuda.stream(gallery.q_stream):
             if r1 > r0:
                 mine[: r1 - r0].copy_(q_host[r0:r1], non_blocking=True)
+            mark("query slice copied", gallery.q_stream)
             ready[0] = dist.all_gather_into_tensor(q_all, mine, group=group, async_op=True)
         q_all.record_stream(gallery.q_stream)
         mine.record_stream(gallery.q_stream)
@@ -212,31 +249,23 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
             if r is not None and not isinstance(r, torch.cuda.Event):
                 r.wait()
         return (torch.full((nq, k), float("-inf"), device=dev), torch.full((nq, k), -1, dtype=torch.int32, device=dev))
-    q16 = torch.empty((q_layout.rows, 512), dtype=torch.bfloat16, device=dev)
+    q16 = q_ready16 if q_ready16 is not None else torch.empty((q_layout.rows, 512), dtype=torch.bfloat16, device=dev)
     vals = torch.empty((len(gallery.chunks), nq, k), dtype=torch.float32, device=dev)
     idxs = torch.empty((len(gallery.chunks), nq, k), dtype=torch.int32, device=dev)
 
-    def issue_copy(c: int):
-        lo, hi, r0, r1, _ = gallery.chunks[c]
-        b = c & 1
-        with torch.cuda.stream(gallery.copy_stream):
-            if c >= 2:
-                gallery.copy_stream.wait_event(gallery.consumed[b])  # K0 of chunk c-2 has read the buffer
-            gallery.stage[b][: r1 - r0].copy_(gallery.rows[r0:r1], non_blocking=True)
-            gallery.copied[b].record(gallery.copy_stream)
-
-    # the staging buffers may still be read by the previous call's K0 on `main` (the function returns device
-    # tensors without synchronising): order this call's first copies behind everything enqueued so far
+    # every chunk's copy is enqueued up front, back to back on the copy stream; the device buffer may still be read
+    # by the previous call's K0 on `main` (the function returns device tensors without synchronising)
     gallery.copy_stream.wait_stream(main)
-    issue_copy(0)
+    with torch.cuda.stream(gallery.copy_stream):
+        for c, (lo, hi, r0, r1, _) in enumerate(gallery.chunks):
+            gallery.stage[r0:r1].copy_(gallery.rows[r0:r1], non_blocking=True)
+            gallery.copied[c].record(gallery.copy_stream)
+            mark(f"chunk {c} copied", gallery.copy_stream)
     for c, (lo, hi, r0, r1, lay) in enumerate(gallery.chunks):
         b = c & 1
-        if c + 1 < len(gallery.chunks):
-            issue_copy(c + 1)
-        main.wait_event(gallery.copied[b])
+        main.wait_event(gallery.copied[c])
         g16 = gallery.op16[b][: r1 - r0]
-        ops.prep(gallery.stage[b][: r1 - r0], lay, out=g16)
-        gallery.consumed[b].record(main)
+        ops.prep(gallery.stage[r0:r1], lay, out=g16)
         # the query parts only matter while they are still arriving: the first gallery chunk is scored part
         # by part, every later chunk against the whole query set in one launch
         todo = parts if c == 0 else [(0, nq, 0, q_layout.rows, q_layout)]
@@ -247,7 +276,9 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
                         main.wait_event(ready[p])
                     else:
                         ready[p].wait()
-                ops.prep(q_dev[qr0:qr1], qlay, out=q16[qr0:qr1])
+                if q_ready16 is None:
+                    ops.prep(q_dev[qr0:qr1], qlay, out=q16[qr0:qr1])
+                mark(f"query part {p} ready")
             if queries_are == "gesture":
                 s = ops.simpool_allpairs(q16[qr0:qr1], qlay, g16, lay, mode)
             else:
@@ -255,9 +286,21 @@ def retrieve_topk_streamed(q_host: torch.Tensor, q_layout: ops.Layout, gallery: 
             v, i = ops.topk(s, k, idx_offset=gallery.idx_base + lo)
             vals[c, qlo:qhi].copy_(v)
             idxs[c, qlo:qhi].copy_(i)
+        mark(f"chunk {c} scored")
     if len(gallery.chunks) == 1:
         return vals[0], idxs[0]
-    return ops.topk_merge(vals, idxs)
+    out = ops.topk_merge(vals, idxs)
+    mark("chunk lists merged")
+    return out
+
+
+def timeline_ms(timeline: dict) -> list:
+    """[(name, milliseconds since "start")] of a timeline filled by retrieve_topk_streamed; call after a synchronise."""
+    ev = timeline.get("events", [])
+    if not ev:
+        return []
+    t0 = ev[0][1]
+    return [(name, round(t0.elapsed_time(e), 3)) for name, e in ev]
 
 
 # ---------------------------------------------------------------------------------------------------------------

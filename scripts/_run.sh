@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "wide or 64 or spot or asd" 2>&1 | tail -4
+timeout 150 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q 2>&1 | grep -E "Error|error|assert|passed|failed|differs" | head -20

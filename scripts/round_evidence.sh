@@ -27,3 +27,7 @@ for tool in memcheck synccheck racecheck initcheck; do
   timeout 900 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_${tool}_$R.log python scripts/sanitize_target.py > gpurun_out/sanitizer_${tool}_$R.out 2>&1
   echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_${tool}_$R.log
 done
+# racecheck once more with single-CTA MMAs: the only hazards the pair build reports sit inside tcgen05.alloc.cta_group::2
+JEGAL_CTA_GROUP=1 timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/sanitizer_racecheck_cta1_$R.log python scripts/sanitize_target.py > gpurun_out/sanitizer_racecheck_cta1_$R.out 2>&1
+tail -2 gpurun_out/sanitizer_racecheck_cta1_$R.log
+python scripts/bench_grouped.py > gpurun_out/stages_$R.jsonl 2> gpurun_out/stages_$R.err
