@@ -334,8 +334,8 @@ def main_ours(args, wl, rank, local_rank, world):
             q_host = streaming.shared_host_tensor(q_shared_path, (Q * T, 512), torch.float16, create=False)
     else:
         q_host = q_raw.cpu().pin_memory()
-    # chunk sizes n x (1, 2, 5, 4, 2, 1, 1) / 16: whichever of copying and scoring is the bottleneck at this N, only
-    # 1/16 of the other is exposed at either end (streaming.balanced_schedule)
+    # sixteen equal chunks: whichever of copying and scoring is the bottleneck at this N, 1/16 of the other is exposed
+    # and no chunk's copy outlasts the scoring of the one before it by much (streaming.balanced_schedule)
     gallery = streaming.StreamedGallery(g_shard.cpu(), np.full(n_shard, W), device=dev, idx_base=lo,
                                         schedule=streaming.balanced_schedule(n_shard))
     qg = ops.QueryGather(Q * T) if world > 1 else None  # C2: fused K0 + NVLink all-gather of the query operand

@@ -41,28 +41,21 @@ def chunk_schedule(n_clips: int, chunk_clips: int, ramp: bool = True):
     return sched
 
 
-def balanced_schedule(n_clips: int, min_clips: int = 128):
-    """Chunk sizes n x (1, 2, 5, 4, 2, 1, 1) / 16: small at BOTH ends, few chunks in between.  The host->device copies
-    run back to back on their own stream and chunk i is scored while chunk i + 1 arrives, so the step costs
-    copy(first chunk) + max(all copies, all scoring) + scoring(last chunk): whichever side is the bottleneck -- scoring
-    at N <= 2 (K1 needs 2x the gallery's PCIe time), the copies at N >= 4 on a host whose eight links share
-    ~236 GB/s (profiles/h2d_ceiling_r02.json: 23 - 36 GB/s per GPU with all eight active) -- only 1/16 of the other
-    side is exposed.  Every further chunk would add a launch tail and a handful of host-side calls."""
+def balanced_schedule(n_clips: int, n_chunks: int = 16, min_clips: int = 128):
+    """`n_chunks` equal chunks.  The host->device copies run back to back on their own stream and chunk i is scored while
+    chunk i + 1 arrives, so the step costs copy(first chunk) + max(all copies, all scoring) + scoring(last chunk) PLUS
+    a bubble whenever a chunk's copy takes longer than the scoring of the chunk before it.  When scoring is the
+    bottleneck (N <= 2: K1 needs 2x the gallery's PCIe time) only the first copy is exposed; when the two rates are
+    close (N = 8 on a host whose eight links share ~236 GB/s, profiles/h2d_ceiling_r02_n8.json: 142 MB take 6.1 ms on
+    the slow links against 5.1 ms of K1) every large chunk stalls the GPU for the difference -- the measured timeline of
+    a (1, 2, 5, 4, 2, 1, 1)/16 schedule showed a 1.3 ms bubble behind its 5/16 chunk (profiles/e2e_timeline_r02_*).
+    Sixteen equal chunks expose 1/16 of either side whatever the ratio; more would only add launch tails."""
     n = int(n_clips)
     if n <= 0:
         return []
-    if n < 16 * min_clips:
-        return [n]
-    sizes = [(n * f) // 16 for f in (1, 2, 5, 4, 2, 1, 1)]
-    sizes[2] += n - sum(sizes)  # rounding goes to the largest chunk
-    out = []
-    for sz in sizes:  # merge chunks below min_clips into their predecessor (tiny galleries)
-        if sz <= 0:
-            continue
-        if out and (sz < min_clips or out[-1] < min_clips):
-            out[-1] += sz
-        else:
-            out.append(sz)
+    k = max(1, min(int(n_chunks), n // max(1, min_clips)))
+    base, extra = divmod(n, k)
+    out = [base + (1 if i < extra else 0) for i in range(k)]
     assert sum(out) == n and min(out) > 0, (n, out)
     return out
 

@@ -15,13 +15,15 @@ Pinning status
     utils/plot_heatmap.py cannot be imported (matplotlib is absent); its
     get_attn_matrix (:34-59) equals evaluate_spotting's minus the F.normalize and
     is pinned through that one.
-  * simpool_* max-pool modes and topk: PARITY UNPINNED by the reference — the
-    released code has no max-pool scoring and no top-k (training loss unreleased,
-    README.md:163-165).  They are restated from the reference's own primitives
-    (F.normalize + torch.mm as at evaluate_spotting.py:49-52, then amax/mean).
-    The mean/mean mode IS pinned: with the per-clip 1/||mean|| scales it must
-    equal get_similarity_matrix on the mean-pooled clips (identity checked in
-    tests/test_oracle_golden.py).
+  * simpool_* pooling modes: the T x W cosine tile is PINNED — tests/golden/simpool_tiles.npz
+    holds tiles produced by the reference's own get_similarity_matrix
+    (evaluate_retrieval.py:38-48: F.normalize + matmul) on per-frame / per-word rows of clip
+    pairs, plus numpy max / mean of those tiles; cos_tile, pool_tile and both simpool_allpairs
+    forms replay them (tests/test_oracle_golden.py).  Only the final amax / mean over a
+    reference-made tile and the top-k order (stable argsort) are restated: the released code
+    has no max-pool scoring and no top-k (training loss unreleased, README.md:163-165), so
+    those two one-liners stay PARITY UNPINNED.  The mean/mean mode is also pinned through the
+    identity with get_similarity_matrix on the mean-pooled clips.
   * word_level_* (models/jegal.py:131-252): PINNED — oracle/make_golden.py extracts the two
     methods' source from models/jegal.py with `ast` (the module itself cannot be imported
     offline: it downloads XLM-R at import, models/jegal.py:13-14) and executes them on synthetic
