@@ -237,7 +237,7 @@ def test_heatmap_renderer_jet_blend_and_png(tmp_path):
     over, base = render.jet(np.array([0.01])), render.jet(np.array([0.05]))
     want = 0.76 * (0.6 * over[0] + 0.4 * base[0]) + 0.24
     assert np.allclose(rgb[0, 0], want)
-    path = render.render_heatmap(attn, ["hello", "world"], fname=str(tmp_path / "hm"), cell=4)
+    path = render.render_heatmap(attn, ["hello", "world"], fname=str(tmp_path / "hm"), cell=4, labels=False)
     raw = open(path, "rb").read()
     assert raw[:8] == b"\x89PNG\r\n\x1a\n"
     w, h = struct.unpack(">II", raw[16:24])
@@ -245,6 +245,21 @@ def test_heatmap_renderer_jet_blend_and_png(tmp_path):
     idat = raw[raw.index(b"IDAT") + 4: raw.index(b"IEND") - 8]
     pix = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
     assert np.array_equal(pix[0, 0], np.rint(want * 255).astype(np.uint8))
+    # with tick labels (plot_heatmap.py:89-92): margins for the words, the frame numbers and the colour-bar scale; the
+    # heat-map cells sit unchanged behind the left margin, and the margins carry dark glyph pixels
+    path = render.render_heatmap(attn, ["hello", "world"], fname=str(tmp_path / "hm2"), cell=16)
+    raw = open(path, "rb").read()
+    w2, h2 = struct.unpack(">II", raw[16:24])
+    left = render.text_width("hello", 2) + 6
+    assert w2 == left + 3 * 16 + 8 + 8 + render.text_width("0.0", 2) + 6 and h2 == 2 * 16 + 22
+    idat = raw[raw.index(b"IDAT") + 4: raw.index(b"IEND") - 8]
+    pix = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h2, 1 + 3 * w2)[:, 1:].reshape(h2, w2, 3)
+    assert np.array_equal(pix[0, left], np.rint(want * 255).astype(np.uint8))
+    assert (pix[:32, :left].sum(axis=2) == 0).sum() > 40 and (pix[32:, left:].sum(axis=2) == 0).sum() > 10
+    img = np.ones((9, 14, 3))
+    render.draw_text(img, 1, 1, "1!", 1)   # glyph check: '1' = 00 42 7F 40 00, '!' = 00 00 5F 00 00 (column bytes)
+    cols = ["".join("#" if img[y, x, 0] < 0.5 else "." for y in range(1, 8)) for x in range(1, 12)]
+    assert cols[2] == "#######" and cols[1] == ".#....#" and cols[8] == "#####.#"
 
 
 def test_pack_rows_host_threaded_equals_concatenate():
