@@ -344,7 +344,9 @@ def main_ours(args, wl, rank, local_rank, world):
     d2h = Q * k * 8
 
     def e2e_step(timeline=None):
-        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_parts=1,
+        # N = 1: the queries travel in 4 parts and the first gallery chunk is scored part by part as they arrive;
+        # N > 1: every rank copies 1/N of the queries and C2 replicates the prepared operand
+        vv, ii = streaming.retrieve_topk_streamed(q_host, q_layout, gallery, k=k, mode=mode, q_parts=4 if world == 1 else 1,
                                                   q_gather=qg if qg is not None else False, timeline=timeline)
         if world > 1:
             vals = torch.empty((world * Q, k), dtype=torch.float32, device=dev)

@@ -7,6 +7,7 @@ import sys
 import numpy as np
 import pandas as pd
 import pytest
+import torch
 
 from oracle import oracle
 
@@ -153,8 +154,20 @@ def test_streamed_spotting_and_asd_equal_resident(pkl_dir):
         ref = scoring.spot_batch(cs.gesture_list(), cs.content_list(), tw, windows=win)
         assert np.array_equal(r["pred_frame"], ref["pred_frame"]) and np.array_equal(r["correct"], ref["correct"])
         assert np.array_equal(r["pred_score"], ref["pred_score"]) and np.array_equal(r["heat"], np.concatenate(ref["heat"]))
+    # fp32 storage: no fused path, every chunk takes one K0 pass (normalise + cast to bf16) in front of K3
+    g32 = streaming.HostClips(torch.from_numpy(np.concatenate(cs.gesture_list()).astype(np.float32)), np.diff(cs.cu_t))
+    c32 = streaming.HostClips(torch.from_numpy(np.concatenate(cs.content_list()).astype(np.float32)), np.diff(cs.cu_w))
+    r32 = streaming.spot_streamed(g32, c32, tw, windows=win, n_chunks=3, want_heat=True)
+    assert np.abs(r32["heat"] - np.concatenate(ref["heat"])).max() < 1.5e-2 and (r32["pred_frame"] == ref["pred_frame"]).mean() > 0.9
     pair_g = np.arange(cs.n, dtype=np.int32)
     pair_c = np.repeat(np.arange(0, cs.n, 6, dtype=np.int32), 6)
+    # pairs listed in an order that does not follow the gesture clips: the per-chunk selection takes the gather route
+    perm = np.random.default_rng(3).permutation(cs.n // 6)
+    pg_s = pair_g.reshape(-1, 6)[perm].reshape(-1)
+    pc_s = pair_c.reshape(-1, 6)[perm].reshape(-1)
+    ref_s = scoring.asd_batch(cs.content_list(), cs.gesture_list(), pg_s, pc_s, 6, mode="max_t_mean_w")
+    r_s = streaming.asd_streamed(g, c, pg_s, pc_s, 6, mode="max_t_mean_w", n_chunks=4)
+    assert np.array_equal(r_s["scores"], ref_s["scores"])
     for mode in ("reference", "max_t_mean_w"):
         ref = scoring.asd_batch(cs.content_list(), cs.gesture_list(), pair_g, pair_c, 6, mode=mode)
         for n_chunks in (1, 5):

@@ -369,3 +369,16 @@ def test_balanced_schedule_covers_every_clip():
         if sch:
             assert max(sch) - min(sch) <= 1
     assert balanced_schedule(8192) == [512] * 16 and balanced_schedule(300) == [150, 150]
+
+
+def test_metrics_from_counts_rejects_nan_diagonal_and_empty():
+    """A NaN ground-truth score (zero-length clip, NaN embedding) makes n_equal = 0 for its row: the reference would
+    silently drop the row from every denominator; here it is an error, and so is an empty matrix."""
+    from jegal_b200.scoring import _metrics_from_counts
+    from jegal_b200._lib import JegalError
+    m = _metrics_from_counts(np.array([0, 3, 7]), np.array([1, 1, 1]))
+    assert m["R1"] == pytest.approx(1 / 3) and m["R5"] == pytest.approx(2 / 3) and m["MR"] == 4.0
+    with pytest.raises(JegalError, match="NaN"):
+        _metrics_from_counts(np.array([0, 3, 7]), np.array([1, 0, 1]))
+    with pytest.raises(JegalError, match="empty"):
+        _metrics_from_counts(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
