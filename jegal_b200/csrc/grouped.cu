@@ -335,6 +335,9 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           JEGAL_GTRACED(0, mbar_wait_lean(t_empty(buf), ((tile / kNumAcc) & 1u) ^ 1u));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kNMax;
+          // a row tile of <= 64 frames is an M = 64 MMA: its A window is 64 rows (8 KB per k-block instead of 16 KB of
+          // shared-memory reads); the accumulator then sits on lanes 0-15 of every 32-lane quarter (rows 16 q .. 16 q + 15)
+          const uint32_t idesc_t = rows <= 64 ? ((idesc & ~(0x1fu << 24)) | (4u << 24)) : idesc;
 #pragma unroll 1
           for (int kb = 0; kb < kNumKBlocks; ++kb) {
             uint32_t need;
@@ -345,7 +348,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
             const uint64_t dC = make_smem_desc_sw128(off + bytes_g);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16<1>(d_tmem, dG + 2u * k, dC + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16<1>(d_tmem, dG + 2u * k, dC + 2u * k, idesc_t, (kb | k) != 0 ? 1u : 0u);
             umma_commit<1>(empty(slot));
             if (++slot == kGStages) {
               slot = 0;
@@ -364,7 +367,6 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
     }
   } else if (warp >= 4 && warp < kNormWarp0) {
     const int q = warp - 4;
-    const int et = q * 32 + lane;  // frame within the row tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t tile = 0, parity = 0;
     unsigned long long tr[4] = {0, 0, 0, 0};
@@ -399,6 +401,10 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
       }
       for (int32_t rt = 0; rt < it.n_rt; ++rt, ++tile) {
         const uint32_t buf = tile % kNumAcc;
+        // frame of this thread within the row tile: lane of a full (M = 128) tile, lanes 0-15 of every quarter for an
+        // M = 64 tile (the issuer's rule: <= 64 frames)
+        const bool m64 = it.T - rt * 128 <= 64;
+        const int et = m64 ? q * 16 + (lane & 15) : q * 32 + lane;
         JEGAL_GTRACED(0, mbar_wait_lean(t_full(buf), (tile / kNumAcc) & 1u));
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_off + buf * kNMax;
@@ -455,7 +461,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         if (lane == 0) mbar_arrive(t_empty(buf));
 
         const int32_t t = rt * 128 + et;
-        const bool valid = t < it.T;
+        const bool valid = t < it.T && !(m64 && lane >= 16);
         if constexpr (kEpi == EPI_SPOT) {
           // softmax over words of s / tau (evaluate_spotting.py:52-54), per frame; only the
           // 16-column groups that hold words are touched (W is uniform across the CTA)
