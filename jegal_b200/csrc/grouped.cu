@@ -16,20 +16,22 @@
 //   warp 1  tcgen05.mma issuer: M = 128, N = roundup16(W), 32 MMAs per row tile
 //   warp 2  TMEM allocator (4 accumulator buffers of 64 columns)
 //   warps 4-7 epilogue: tcgen05.ld -> softmax / pooling -> coalesced stores
-//   warps 8-15 (kFuse only) row norms: the L2 normalisation of the reference
+//   warps 8-11 (kFuse only) a second epilogue warpgroup (the two groups take the items alternately)
+//   warps 12-19 (kFuse only) row norms: the L2 normalisation of the reference
 //           (F.normalize at evaluate_spotting.py:49-50, CosineSimilarity's clamped norms at
 //           evaluate_asd.py:45-47) is FUSED INTO THE LOAD: the operands are the rows exactly as
 //           the .pkl stores them (fp16, or bf16), TMA stages them once, the tensor core contracts
 //           the raw rows, and these warps re-read the staged k-blocks from shared memory (a row's
 //           128 bytes stay inside its own swizzled line, so a sum of squares needs no
-//           un-swizzling): norm warp k owns k-block k of every row tile, adds its partial
-//           sum(x^2) of every frame / word into a per-tile table, and the epilogue scales lane
+//           un-swizzling): norm warp w owns k-block w of every row tile, stores its partial
+//           sum(x^2) of every frame / word into per-k-block tables, and the epilogue scales lane
 //           (frame) and column (word) by rsqrt(max(sum, eps^2)) = 1 / max(||row||, eps).
 //           No normalised copy of the operands ever exists in HBM: bytes per clip are the
 //           (T + W) x 1 KB of the stored rows, read once.
 //           (One warp per k-block, not one warp per row range of every k-block: a warp walks the
 //           stage sequence serially -- wait, load, arrive -- at ~700 cycles per iteration whatever
-//           the payload, measured with JEGAL_GROUPED_TRACE; eight warps take one stage in eight.)
+//           the payload, measured with JEGAL_GROUPED_TRACE; eight warps take one stage in eight.
+//           640 threads: setmaxnreg moves registers from the producer / norm warpgroups to the epilogue's.)
 //
 // Items are dealt round-robin to a persistent grid of one CTA per SM.
 #include <cuda_fp16.h>
@@ -47,13 +49,14 @@ using namespace ptx;
 namespace {
 
 constexpr int kGThreads = 256;
-constexpr int kGThreadsFuse = 512;                // + 8 row-norm warps, one per k-block
-constexpr int kNormWarp0 = 8;
+constexpr int kGThreadsFuse = 640;                // + a second epilogue warpgroup and 8 row-norm warps
+constexpr int kNormWarp0 = 12;                    // kFuse: warps 4-7 / 8-11 epilogue groups, 12-15 row norms
+constexpr int kNormWarps = 8;                     // norm warp w owns k-block w of every row tile
 constexpr int kNormTables = 2;                    // tile parity
 constexpr int kNormRows = 192;                    // per accumulator buffer: 128 frame slots + 64 word slots
 constexpr int kGStages = 32;                     // barrier slots; smem is a BYTE ring (see RingAlloc)
 constexpr int kNMax = 64;                        // words per clip on the N side
-constexpr uint32_t kGRingBytes = 208 * 1024;     // operand ring: a stage takes only the bytes it loads
+constexpr uint32_t kGRingBytes = 206 * 1024;     // operand ring: a stage takes only the bytes it loads
 constexpr int kNumAcc = 4;
 constexpr uint32_t kGTmemCols = kNumAcc * kNMax;  // 256
 constexpr int kBoxG = 32, kBoxC = 16;
@@ -153,7 +156,7 @@ struct RingAlloc {
 #define JEGAL_GTRACE_ON(p) false
 #endif
 
-__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_epi(uint32_t grp) { asm volatile("bar.sync %0, 128;" ::"r"(1u + grp) : "memory"); }
 
 // sum of squares of the 8 16-bit values of one 16-byte chunk, accumulated in fp32.
 // kImpl 0: widen to fp32 (HADD2.F32 / a shift for bf16) + FFMA; kImpl 1: the mixed-precision fma of sm_100
@@ -212,19 +215,19 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   auto t_empty = [&](int b) { return bars + 8u * (2 * kGStages + kNumAcc + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * kGStages + 2 * kNumAcc);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
-  // epilogue scratch (after the tmem slot), double-buffered by item parity so one named barrier
-  // per item suffices: per parity 4 warps x 64 floats + 4 floats + 4 ints
+  // epilogue scratch (after the tmem slot), per epilogue warpgroup, double-buffered by item parity so one named
+  // barrier per item suffices: per (group, parity) 4 warps x 64 floats + 4 floats + 4 ints
   constexpr int kScratchF = 4 * kNMax + 4;
   float* epi_f0 = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw_addr));
-  int32_t* epi_i0 = reinterpret_cast<int32_t*>(epi_f0 + 2 * kScratchF);
-  volatile uint32_t* need_smem = reinterpret_cast<volatile uint32_t*>(epi_i0 + 8);  // [kGStages], producer-private
+  int32_t* epi_i0 = reinterpret_cast<int32_t*>(epi_f0 + 4 * kScratchF);
+  volatile uint32_t* need_smem = reinterpret_cast<volatile uint32_t*>(epi_i0 + 16);  // [kGStages], producer-private
   // kFuse: partial sums of squares of a tile's rows, one table per (tile parity, k-block): [tb][kb][0..127] frames,
   // [tb][kb][128..191] words (plain stores: fp32 shared-memory atomics are a CAS loop, 14 % of the kernel's stall
   // samples when the eight k-block warps added into one table); inv_w: per epilogue warp, the 64 inverse word
   // norms of the tile it is draining
   float* part = reinterpret_cast<float*>(const_cast<uint32_t*>(need_smem) + kGStages);
   float* inv_w = part + kNormTables * kNumKBlocks * kNormRows;
-  const uint32_t n_full0 = smem_u32(inv_w + 4 * kNMax);
+  const uint32_t n_full0 = smem_u32(inv_w + 8 * kNMax);
   auto n_full = [&](int b) { return n_full0 + 8u * b; };                   // all 8 partial tables of a tile are written
   auto n_empty = [&](int b) { return n_full0 + 8u * (kNormTables + b); };  // the 4 epilogue warps have read them
 
@@ -257,6 +260,11 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Role dispatch by warpgroup.  kFuse: 640 threads, i.e. 96 registers per thread, which is why the epilogue works on
+  // one 16-column group of the accumulator at a time instead of holding all 64 columns.  (setmaxnreg was tried to move
+  // registers from the producer / row-norm warpgroups to the epilogue's: this ptxas caps the whole kernel at the
+  // SMALLEST setmaxnreg value it sees, whatever dominates what, so it only made things worse.)
+  if (warp < 4) {
   if (warp == 0) {
     // (Two producer threads -- frame boxes from warp 0, word boxes from warp 3, barrier count 2 -- were measured:
     // no gain, 0.33 vs 0.31 ms on config 3; the producer's issue path is not what paces the kernel.)
@@ -365,20 +373,32 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         g[4] = static_cast<unsigned long long>(clock64() - t_begin);
       }
     }
-  } else if (warp >= 4 && warp < kNormWarp0) {
-    const int q = warp - 4;
+  }
+  } else if (warp < (kFuse != 0 ? kNormWarp0 : 8)) {
+  {
+    // Epilogue.  kFuse: TWO warpgroups (warps 4-7 and 8-11) take the items alternately -- with the scaling by the
+    // row norms in front of the softmax one warpgroup needed ~4400 cycles per clip of dependent instructions against
+    // the ~3400 cycles a clip may take at the HBM roofline (JEGAL_GROUPED_TRACE: the epilogue never waited).
+    const int q = (warp - 4) & 3;
+    const uint32_t grp = static_cast<uint32_t>(warp - 4) >> 2;
+    constexpr uint32_t kGroups = kFuse != 0 ? 2u : 1u;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t tile = 0, parity = 0;
+    uint32_t tile = 0, seq = 0;
     unsigned long long tr[4] = {0, 0, 0, 0};
     const long long t_begin = JEGAL_GTRACE_ON(p) ? clock64() : 0;
     (void)tr;
     (void)t_begin;
     Item nxt = load_item(p, min(static_cast<int32_t>(blockIdx.x), p.n_items - 1));
-    for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x, parity ^= 1u) {
+    for (int32_t i = blockIdx.x; i < p.n_items; i += gridDim.x, ++seq) {
       const Item it = nxt;
       nxt = load_item(p, min(i + static_cast<int32_t>(gridDim.x), p.n_items - 1));
-      float* epi_f = epi_f0 + parity * kScratchF;
-      int32_t* epi_i = epi_i0 + parity * 4;
+      if (kGroups > 1 && (seq % kGroups) != grp) {  // the other warpgroup's item
+        tile += static_cast<uint32_t>(it.n_rt);
+        continue;
+      }
+      const uint32_t parity = (seq / kGroups) & 1u;
+      float* epi_f = epi_f0 + (grp * 2 + parity) * kScratchF;
+      int32_t* epi_i = epi_i0 + (grp * 2 + parity) * 4;
       // per-item state; every scalar the finalisation needs is fetched now, not after the barrier
       float best_v = -1.0f;
       int32_t best_t = 0x7fffffff;
@@ -408,20 +428,8 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         JEGAL_GTRACED(0, mbar_wait_lean(t_full(buf), (tile / kNumAcc) & 1u));
         tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_off + buf * kNMax;
-        uint32_t v[kNMax];
-#pragma unroll
-        for (int g = 0; g < kNMax / 16; ++g) {
-          if (g < it.n16) {
-            uint32_t r[16];
-            tmem_ld_32x16(t_addr + g * 16, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[g * 16 + j] = r[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[g * 16 + j] = 0u;
-          }
-        }
-        tmem_ld_wait();
+        float ig = 1.0f;
+        const float* iw = nullptr;
         if constexpr (kFuse != 0) {
           // cos[t, w] = (g_t . c_w) / (max(||g_t||, eps) max(||c_w||, eps)): the row-norm warps summed the squares of
           // the very bytes the MMAs consumed; 1 / max(sqrt(s), eps) = rsqrt(max(s, eps^2))
@@ -436,117 +444,149 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
             sw0 += pt_[k * kNormRows + 128 + lane];
             sw1 += pt_[k * kNormRows + 160 + lane];
           }
-          const float ig = rsqrtf(fmaxf(sf, eps2));
-          float* iw = inv_w + q * kNMax;
-          iw[lane] = rsqrtf(fmaxf(sw0, eps2));
-          iw[32 + lane] = rsqrtf(fmaxf(sw1, eps2));
+          ig = rsqrtf(fmaxf(sf, eps2));
+          float* iw_w = inv_w + (grp * 4 + q) * kNMax;
+          iw_w[lane] = rsqrtf(fmaxf(sw0, eps2));
+          iw_w[32 + lane] = rsqrtf(fmaxf(sw1, eps2));
           mbar_arrive(n_empty(tb));  // this lane has read its entries of the partial tables
           __syncwarp();              // inv_w is complete before anyone reads it
-#pragma unroll
-          for (int g = 0; g < kNMax / 16; ++g) {
-            if (g < it.n16) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 ic = *reinterpret_cast<const float4*>(iw + g * 16 + j);
-                v[g * 16 + j] = __float_as_uint(__uint_as_float(v[g * 16 + j]) * ig * ic.x);
-                v[g * 16 + j + 1] = __float_as_uint(__uint_as_float(v[g * 16 + j + 1]) * ig * ic.y);
-                v[g * 16 + j + 2] = __float_as_uint(__uint_as_float(v[g * 16 + j + 2]) * ig * ic.z);
-                v[g * 16 + j + 3] = __float_as_uint(__uint_as_float(v[g * 16 + j + 3]) * ig * ic.w);
-              }
-            }
-          }
+          iw = iw_w;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty(buf));
+        // One 16-column group of the accumulator at a time (load, scale by the row norms): 16 live values per thread
+        // instead of 64, which is what lets 640 threads (two epilogue warpgroups + eight norm warps) fit the register
+        // file; clips of <= 16 words -- the usual case -- still see a single TMEM load.
+        auto load_group = [&](int g, float (&x)[16]) {
+          uint32_t r[16];
+          tmem_ld_32x16(t_addr + g * 16, r);
+          tmem_ld_wait();
+          if constexpr (kFuse != 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 ic = *reinterpret_cast<const float4*>(iw + g * 16 + j);
+              x[j] = __uint_as_float(r[j]) * ig * ic.x;
+              x[j + 1] = __uint_as_float(r[j + 1]) * ig * ic.y;
+              x[j + 2] = __uint_as_float(r[j + 2]) * ig * ic.z;
+              x[j + 3] = __uint_as_float(r[j + 3]) * ig * ic.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(r[j]);
+          }
+        };
+        auto release = [&]() {  // the accumulator buffer goes back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty(buf));
+        };
 
         const int32_t t = rt * 128 + et;
         const bool valid = t < it.T && !(m64 && lane >= 16);
         if constexpr (kEpi == EPI_SPOT) {
-          // softmax over words of s / tau (evaluate_spotting.py:52-54), per frame; only the
-          // 16-column groups that hold words are touched (W is uniform across the CTA)
-          float m = -INFINITY;
+          // softmax over words of s / tau (evaluate_spotting.py:52-54), per frame
+          float pt = 0.f;
+          if (it.n16 == 1) {  // W <= 16: everything in registers
+            float x[16];
+            load_group(0, x);
+            release();
+            float m = -INFINITY;
 #pragma unroll
-          for (int g = 0; g < kNMax / 16; ++g) {
-            if (g < it.n16) {
+            for (int j = 0; j < 16; ++j)
+              if (j < it.W) m = fmaxf(m, x[j]);
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < it.W) {
+                x[j] = __expf((x[j] - m) * p.inv_tau);
+                den += x[j];
+                if (j == target) pt = x[j];
+              }
+            }
+            const float inv_den = 1.0f / den;
+            pt *= inv_den;
+            if (valid && fh) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (g * 16 + j < it.W) m = fmaxf(m, __uint_as_float(v[g * 16 + j]));
+                if (j < it.W) fh[static_cast<int64_t>(j) * it.T + t] = x[j] * inv_den;
             }
-          }
-          float den = 0.f, pt = 0.f;
+          } else {  // up to 64 words: three passes over the accumulator's column groups (TMEM reads are cheap)
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int g = 0; g < it.n16; ++g) {
+              float x[16];
+              load_group(g, x);
 #pragma unroll
-          for (int g = 0; g < kNMax / 16; ++g) {
-            if (g < it.n16) {
+              for (int j = 0; j < 16; ++j)
+                if (g * 16 + j < it.W) m = fmaxf(m, x[j]);
+            }
+            float den = 0.f;
+#pragma unroll 1
+            for (int g = 0; g < it.n16; ++g) {
+              float x[16];
+              load_group(g, x);
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int w = g * 16 + j;
                 if (w < it.W) {
-                  const float e = __expf((__uint_as_float(v[w]) - m) * p.inv_tau);
-                  v[w] = __float_as_uint(e);
+                  const float e = __expf((x[j] - m) * p.inv_tau);
                   den += e;
                   if (w == target) pt = e;
                 }
               }
             }
-          }
-          const float inv_den = 1.0f / den;
-          pt *= inv_den;
-          if (valid) {
-            if (p.heat) p.heat[it.g_row0 + t] = pt;
+            const float inv_den = 1.0f / den;
+            pt *= inv_den;
             if (fh) {
-#pragma unroll
-              for (int g = 0; g < kNMax / 16; ++g) {
-                if (g < it.n16) {
+#pragma unroll 1
+              for (int g = 0; g < it.n16; ++g) {
+                float x[16];
+                load_group(g, x);
+                if (valid) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     const int w = g * 16 + j;
-                    if (w < it.W) fh[static_cast<int64_t>(w) * it.T + t] = __uint_as_float(v[w]) * inv_den;
+                    if (w < it.W) fh[static_cast<int64_t>(w) * it.T + t] = __expf((x[j] - m) * p.inv_tau) * inv_den;
                   }
                 }
               }
             }
+            release();
+          }
+          if (valid) {
+            if (p.heat) p.heat[it.g_row0 + t] = pt;
             if (pt > best_v) {  // frames arrive in increasing order: strict > keeps the first maximum
               best_v = pt;
               best_t = t;
             }
           }
         } else {
-          if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
-            // max over frames first: per word, reduce across the warp's valid lanes
+          float c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? 0.f : -INFINITY;
+#pragma unroll 1
+          for (int g = 0; g < it.n16; ++g) {
+            float x[16];
+            load_group(g, x);
+            if (g == it.n16 - 1) release();
+            if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
+              // max over frames first: per word, reduce across the warp's valid lanes
 #pragma unroll
-            for (int g = 0; g < kNMax / 16; ++g) {
-              if (g < it.n16) {
+              for (int j = 0; j < 16; ++j) {
+                const int w = g * 16 + j;
+                if (w < it.W) {
+                  float y = valid ? x[j] : -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int w = g * 16 + j;
-                  if (w < it.W) {
-                    float x = valid ? __uint_as_float(v[w]) : -INFINITY;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-                    if (lane == (w & 31)) {
-                      if (w < 32) wmax0 = fmaxf(wmax0, x); else wmax1 = fmaxf(wmax1, x);
-                    }
+                  for (int o = 16; o > 0; o >>= 1) y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, o));
+                  if (lane == (w & 31)) {
+                    if (w < 32) wmax0 = fmaxf(wmax0, y); else wmax1 = fmaxf(wmax1, y);
                   }
                 }
               }
-            }
-          } else {
-            float c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? 0.f : -INFINITY;
+            } else {
 #pragma unroll
-            for (int g = 0; g < kNMax / 16; ++g) {
-              if (g < it.n16) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  if (g * 16 + j < it.W) {
-                    const float x = __uint_as_float(v[g * 16 + j]);
-                    c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? c + x : fmaxf(c, x);
-                  }
-                }
+              for (int j = 0; j < 16; ++j) {
+                if (g * 16 + j < it.W) c = p.pool_mode == JEGAL_POOL_MEAN_MEAN ? c + x[j] : fmaxf(c, x[j]);
               }
             }
-            if (valid) racc = p.pool_mode == JEGAL_POOL_MAX_MAX ? fmaxf(racc, c) : racc + c;
           }
+          if (p.pool_mode != JEGAL_POOL_MAX_T_MEAN_W && valid) racc = p.pool_mode == JEGAL_POOL_MAX_MAX ? fmaxf(racc, c) : racc + c;
         }
       }
       // ---- per-item finalisation across the 4 epilogue warps
@@ -564,7 +604,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           epi_f[4 * kNMax + q] = best_v;
           epi_i[q] = best_t;
         }
-        bar_sync_epi();
+        bar_sync_epi(grp);
         if (q == 0 && lane == 0) {
           float bv = epi_f[4 * kNMax];
           int32_t bt = epi_i[0];
@@ -587,7 +627,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         if (p.pool_mode == JEGAL_POOL_MAX_T_MEAN_W) {
           epi_f[q * kNMax + lane] = wmax0;
           epi_f[q * kNMax + 32 + lane] = wmax1;
-          bar_sync_epi();
+          bar_sync_epi(grp);
           if (q == 0) {
             float s = 0.f;
 #pragma unroll
@@ -612,7 +652,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
             racc = is_max ? fmaxf(racc, ov) : racc + ov;
           }
           if (lane == 0) epi_f[4 * kNMax + q] = racc;
-          bar_sync_epi();
+          bar_sync_epi(grp);
           if (q == 0 && lane == 0) {
             float r = epi_f[4 * kNMax];
             for (int w = 1; w < 4; ++w) r = is_max ? fmaxf(r, epi_f[4 * kNMax + w]) : r + epi_f[4 * kNMax + w];
@@ -624,16 +664,16 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
         }
       }
     }
-    if (JEGAL_GTRACE_ON(p) && q == 0 && lane == 0) {
+    if (JEGAL_GTRACE_ON(p) && q == 0 && lane == 0 && grp == 0) {
       unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
       g[5] = tr[0];
       g[6] = tr[1];
       g[7] = static_cast<unsigned long long>(clock64() - t_begin);
     }
   }
-
+  } else {
   if constexpr (kFuse != 0) {
-    if (warp >= kNormWarp0) {
+    {
       // ---- row norms, fused into the load.  Norm warp kb owns k-block kb of every row tile: stage 8 * tile + kb.
       // A stage is [frames: nb x 32 rows][words: n16 x 16 rows] of 128-byte swizzled lines, walked in units of
       // 16 rows: lanes l and l + 16 share row l & 15, one takes the row's 16-byte chunks 0-3, the other 4-7
@@ -641,7 +681,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
       // lanes of every shared-memory phase touch eight different bank groups.
       constexpr bool kBf16 = kFuse == 2;
       constexpr int kImpl = kFuse == 3 ? 0 : 1;
-      const int kb = warp - kNormWarp0;
+      const int nw = warp - kNormWarp0;
       const int r16 = lane & 15;
       const int half = (r16 & 1) ^ (lane >> 4);
       uint32_t lane_off[4];  // byte offset of this lane's four chunks inside a unit
@@ -663,58 +703,66 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           const int32_t rows_g = ((rows + kBoxG - 1) / kBoxG) * kBoxG;
           const int32_t nunits = (rows_g >> 4) + it.n16;  // <= 12
           const uint32_t bytes = static_cast<uint32_t>(nunits) * 2048u;
-          // every role replays the same ring placement; this warp only touches its own stage
-          uint32_t my_off = 0;
+          // every role replays the same ring placement; this warp only touches its own two stages
+          constexpr int kPasses = kNumKBlocks / kNormWarps;
+          uint32_t my_off[kPasses];
 #pragma unroll
           for (int k = 0; k < kNumKBlocks; ++k) {
             uint32_t need;
             const uint32_t o = ring.place(bytes, need);
-            if (k == kb) my_off = o;
+#pragma unroll
+            for (int ps = 0; ps < kPasses; ++ps)
+              if (k == nw + ps * kNormWarps) my_off[ps] = o;
           }
-          const uint32_t stage = tile * kNumKBlocks + static_cast<uint32_t>(kb);
-          const uint32_t slot = stage % kGStages, phase = (stage / kGStages) & 1u;
-          const uint32_t a0 = base + my_off;
           const uint32_t tb = tile % kNormTables;
-          float* dst = part + (tb * kNumKBlocks + kb) * kNormRows;
-          // this warp's table of the tile two tiles back has been read by all four epilogue warps
+          // this tile's tables were last used two tiles back: all four warps of the epilogue group that drained
+          // that tile have read them
           JEGAL_GTRACED(1, mbar_wait_lean(n_empty(tb), ((tile / kNormTables) & 1u) ^ 1u));
-          JEGAL_GTRACED(0, mbar_wait_lean(full(slot), phase));
-          // a ROLLED loop over the stage's 16-row units (two in flight): the body is ~50 instructions and the
-          // kernel's hot code has to fit the instruction cache
           // frame units that lie entirely past the clip's last frame (the box is rounded up to 32 rows) are skipped
           const int32_t units_g = (rows + 15) >> 4;
           const int32_t nwork = units_g + it.n16;
-          float* d = dst + r16;
+#pragma unroll 1
+          for (int pass = 0; pass < kPasses; ++pass) {
+            const int kb = nw + pass * kNormWarps;
+            const uint32_t stage = tile * kNumKBlocks + static_cast<uint32_t>(kb);
+            const uint32_t slot = stage % kGStages, phase = (stage / kGStages) & 1u;
+            const uint32_t a0 = base + my_off[pass];
+            float* d = part + (tb * kNumKBlocks + kb) * kNormRows + r16;
+            JEGAL_GTRACED(0, mbar_wait_lean(full(slot), phase));
+            // a ROLLED loop over the stage's 16-row units (two in flight): the body is ~50 instructions and the
+            // kernel's hot code has to fit the instruction cache
 #pragma unroll 2
-          for (int32_t u = 0; u < nwork; ++u) {
-            const bool is_word = u >= units_g;
-            const int32_t row0 = is_word ? rows_g + (u - units_g) * 16 : u * 16;  // first row of the unit in the stage
-            const uint32_t au = a0 + static_cast<uint32_t>(row0) * 128u;
-            const uint4 x0 = lds128(au + lane_off[0]), x1 = lds128(au + lane_off[1]);
-            const uint4 x2 = lds128(au + lane_off[2]), x3 = lds128(au + lane_off[3]);
-            const float s0 = sumsq8<kBf16, kImpl>(x0, 0.f), s1 = sumsq8<kBf16, kImpl>(x1, 0.f);
-            const float s2 = sumsq8<kBf16, kImpl>(x2, 0.f), s3 = sumsq8<kBf16, kImpl>(x3, 0.f);
-            float ss = (s0 + s1) + (s2 + s3);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-            if (lane < 16) d[is_word ? 128 + (u - units_g) * 16 : row0] = ss;
+            for (int32_t u = 0; u < nwork; ++u) {
+              const bool is_word = u >= units_g;
+              const int32_t row0 = is_word ? rows_g + (u - units_g) * 16 : u * 16;  // first row of the unit in the stage
+              const uint32_t au = a0 + static_cast<uint32_t>(row0) * 128u;
+              const uint4 x0 = lds128(au + lane_off[0]), x1 = lds128(au + lane_off[1]);
+              const uint4 x2 = lds128(au + lane_off[2]), x3 = lds128(au + lane_off[3]);
+              const float s0 = sumsq8<kBf16, kImpl>(x0, 0.f), s1 = sumsq8<kBf16, kImpl>(x1, 0.f);
+              const float s2 = sumsq8<kBf16, kImpl>(x2, 0.f), s3 = sumsq8<kBf16, kImpl>(x3, 0.f);
+              float ss = (s0 + s1) + (s2 + s3);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+              if (lane < 16) d[is_word ? 128 + (u - units_g) * 16 : row0] = ss;
+            }
+            if (lane < 16) mbar_arrive(n_full(tb));  // this lane's table entries of k-block kb are written
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(slot));  // every lane's shared-memory reads of the stage have returned
           }
-          if (lane < 16) mbar_arrive(n_full(tb));  // this lane's table entries are written
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty(slot));  // every lane's shared-memory reads of the stage have returned
         }
       }
       if (JEGAL_GTRACE_ON(p) && lane == 0) {
         unsigned long long* g = p.trace + static_cast<size_t>(blockIdx.x) * 16;
-        if (kb == 0) {
+        if (nw == 0) {
           g[8] = tr[0];
           g[9] = tr[1];
           g[10] = static_cast<unsigned long long>(clock64() - t_begin);
-        } else if (kb == 7) {
+        } else if (nw == kNormWarps - 1) {
           g[11] = tr[0];
           g[12] = tr[1];
         }
       }
     }
+  }
   }
 
   tc_fence_before();
@@ -724,8 +772,8 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
 
 constexpr size_t grouped_smem_bytes() {
   return 1024 + static_cast<size_t>(kGRingBytes) + 8 * (2 * kGStages + 2 * kNumAcc) + 16 +
-         2 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + sizeof(uint32_t) * kGStages + 16 +
-         sizeof(float) * (kNormTables * kNumKBlocks * kNormRows + 4 * kNMax) + 8 * 2 * kNormTables;  // kFuse: partial squared norms, inverse word norms, barriers
+         4 * (sizeof(float) * (4 * kNMax + 4) + sizeof(int32_t) * 4) + sizeof(uint32_t) * kGStages + 16 +
+         sizeof(float) * (kNormTables * kNumKBlocks * kNormRows + 8 * kNMax) + 8 * 2 * kNormTables;  // kFuse: partial squared norms, inverse word norms, barriers
 }
 
 // one thread per group: softmax(scores / tau) within the group + first argmax
