@@ -266,8 +266,8 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   // SMALLEST setmaxnreg value it sees, whatever dominates what, so it only made things worse.)
   if (warp < 4) {
   if (warp == 0) {
-    // (Two producer threads -- frame boxes from warp 0, word boxes from warp 3, barrier count 2 -- were measured:
-    // no gain, 0.33 vs 0.31 ms on config 3; the producer's issue path is not what paces the kernel.)
+    // (Two producer threads -- frame boxes from warp 0, word boxes from warp 3, barrier count 2 -- were measured twice,
+    // before and after the epilogue / norm warps stopped being the limit: 0.33 vs 0.31 ms on config 3 both times.)
     if (elect_one()) {
       const uint64_t pol = policy_evict_first();  // every operand byte is used once
       // stage n uses barrier slot n % kGStages; `inflight` = ring bytes of stages not yet released.
