@@ -60,6 +60,11 @@ constexpr uint32_t kGRingBytes = 206 * 1024;     // operand ring: a stage takes 
 constexpr int kNumAcc = 4;
 constexpr uint32_t kGTmemCols = kNumAcc * kNMax;  // 256
 constexpr int kBoxG = 32, kBoxC = 16;
+// k-blocks per pipeline stage.  The single producer thread spends ~400 cycles of ring / barrier bookkeeping per stage
+// next to ~40 cycles per TMA issue (JEGAL_GROUPED_TRACE: it was busy 87 % of the fused K3 and every other role waited
+// for it); two k-blocks per stage halve that cost -- and the MMA issuer's and the norm warps' barrier traffic.
+constexpr uint32_t kKPerStage = 2;
+constexpr int kStagesPerTile = kNumKBlocks / kKPerStage;
 
 enum GroupedEpi : int { EPI_SPOT = 0, EPI_POOL = 1 };
 
@@ -120,11 +125,14 @@ __device__ __forceinline__ Item load_item(const GroupedParams& p, int32_t i) {
 struct RingAlloc {
   uint32_t w = 0;
   // returns the offset of a stage of `sz` bytes; `need` = bytes consumed including the wrap skip
-  __device__ __forceinline__ uint32_t place(uint32_t sz, uint32_t& need) {
+  // `kb_bytes` = bytes of ONE k-block (frames + words); a stage holds kKPerStage of them back to back
+  __device__ __forceinline__ uint32_t place(uint32_t kb_bytes, uint32_t& need) {
     uint32_t skip = 0;
-    // the MMA always reads 128 frame rows (16 KB) from the stage start, whatever was loaded:
+    const uint32_t sz = kKPerStage * kb_bytes;
+    // the MMA always reads 128 frame rows (16 KB) from the start of every k-block, whatever was loaded:
     // keep that window inside the ring (rows past the clip feed accumulator lanes nobody reads)
-    const uint32_t span = sz > 16384u ? sz : 16384u;
+    const uint32_t win = (kKPerStage - 1) * kb_bytes + 16384u;
+    const uint32_t span = sz > win ? sz : win;
     if (w + span > kGRingBytes) {
       skip = kGRingBytes - w;
       w = 0;
@@ -238,7 +246,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kGStages; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(empty(s), kFuse ? 2 : 1);  // the MMAs' commit (+ the row-norm warp that owns the k-block)
+      mbar_init(empty(s), kFuse ? 1 + kKPerStage : 1);  // the MMAs' commit (+ the row-norm warps that own its k-blocks)
     }
     for (int b = 0; b < kNumAcc; ++b) {
       mbar_init(t_full(b), 1);
@@ -292,7 +300,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           const uint32_t bytes = bytes_g + it.n16 * (kBoxC * 128);
           const int32_t g_row = it.g_row0 + rt * 128;
 #pragma unroll 1
-          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+          for (int st = 0; st < kStagesPerTile; ++st) {
             uint32_t need;
             const uint32_t off = base + ring.place(bytes, need);
             // free ring space / a barrier slot by retiring the oldest stages (the MMAs release in order)
@@ -309,9 +317,13 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
             inflight += need;
             ++n_out;
             const uint32_t fb = full(slot);
-            mbar_arrive_expect_tx(fb, bytes);
-            tma_load_2d(tmG, fb, off, kb * kBlockK, g_row, pol);
-            tma_load_2d(tmC, fb, off + bytes_g, kb * kBlockK, it.c_row0, pol);
+            mbar_arrive_expect_tx(fb, kKPerStage * bytes);
+#pragma unroll
+            for (uint32_t h = 0; h < kKPerStage; ++h) {
+              const int32_t kcol = (st * static_cast<int32_t>(kKPerStage) + static_cast<int32_t>(h)) * kBlockK;
+              tma_load_2d(tmG, fb, off + h * bytes, kcol, g_row, pol);
+              tma_load_2d(tmC, fb, off + h * bytes + bytes_g, kcol, it.c_row0, pol);
+            }
             if (++slot == kGStages) slot = 0;
           }
         }
@@ -347,16 +359,19 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           // shared-memory reads); the accumulator then sits on lanes 0-15 of every 32-lane quarter (rows 16 q .. 16 q + 15)
           const uint32_t idesc_t = rows <= 64 ? ((idesc & ~(0x1fu << 24)) | (4u << 24)) : idesc;
 #pragma unroll 1
-          for (int kb = 0; kb < kNumKBlocks; ++kb) {
+          for (int st = 0; st < kStagesPerTile; ++st) {
             uint32_t need;
             const uint32_t off = base + ring.place(bytes, need);
             JEGAL_GTRACED(1, mbar_wait_lean(full(slot), phase));
             tc_fence_after();
-            const uint64_t dG = make_smem_desc_sw128(off);
-            const uint64_t dC = make_smem_desc_sw128(off + bytes_g);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16<1>(d_tmem, dG + 2u * k, dC + 2u * k, idesc_t, (kb | k) != 0 ? 1u : 0u);
+            for (uint32_t h = 0; h < kKPerStage; ++h) {
+              const uint64_t dG = make_smem_desc_sw128(off + h * bytes);
+              const uint64_t dC = make_smem_desc_sw128(off + h * bytes + bytes_g);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16<1>(d_tmem, dG + 2u * k, dC + 2u * k, idesc_t, (st | static_cast<int>(h) | k) != 0 ? 1u : 0u);
+            }
             umma_commit<1>(empty(slot));
             if (++slot == kGStages) {
               slot = 0;
@@ -707,12 +722,14 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
           constexpr int kPasses = kNumKBlocks / kNormWarps;
           uint32_t my_off[kPasses];
 #pragma unroll
-          for (int k = 0; k < kNumKBlocks; ++k) {
+          for (int st = 0; st < kStagesPerTile; ++st) {
             uint32_t need;
             const uint32_t o = ring.place(bytes, need);
 #pragma unroll
-            for (int ps = 0; ps < kPasses; ++ps)
-              if (k == nw + ps * kNormWarps) my_off[ps] = o;
+            for (int ps = 0; ps < kPasses; ++ps) {
+              const int kb = nw + ps * kNormWarps;
+              if (st == kb / static_cast<int>(kKPerStage)) my_off[ps] = o + static_cast<uint32_t>(kb % static_cast<int>(kKPerStage)) * bytes;
+            }
           }
           const uint32_t tb = tile % kNormTables;
           // this tile's tables were last used two tiles back: all four warps of the epilogue group that drained
@@ -724,7 +741,7 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
 #pragma unroll 1
           for (int pass = 0; pass < kPasses; ++pass) {
             const int kb = nw + pass * kNormWarps;
-            const uint32_t stage = tile * kNumKBlocks + static_cast<uint32_t>(kb);
+            const uint32_t stage = tile * kStagesPerTile + static_cast<uint32_t>(kb) / kKPerStage;
             const uint32_t slot = stage % kGStages, phase = (stage / kGStages) & 1u;
             const uint32_t a0 = base + my_off[pass];
             float* d = part + (tb * kNumKBlocks + kb) * kNormRows + r16;
