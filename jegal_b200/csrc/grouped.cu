@@ -63,7 +63,11 @@ constexpr int kBoxG = 32, kBoxC = 16;
 // k-blocks per pipeline stage.  The single producer thread spends ~400 cycles of ring / barrier bookkeeping per stage
 // next to ~40 cycles per TMA issue (JEGAL_GROUPED_TRACE: it was busy 87 % of the fused K3 and every other role waited
 // for it); two k-blocks per stage halve that cost -- and the MMA issuer's and the norm warps' barrier traffic.
-constexpr uint32_t kKPerStage = 2;
+// Config 3, fused: 1 -> 0.305 ms, 2 -> 0.255-0.260 ms, 4 -> 0.285 ms (stages of up to 96 KB: the 206 KB ring holds too few).
+#ifndef JEGAL_KPER
+#define JEGAL_KPER 2
+#endif
+constexpr uint32_t kKPerStage = JEGAL_KPER;
 constexpr int kStagesPerTile = kNumKBlocks / kKPerStage;
 
 enum GroupedEpi : int { EPI_SPOT = 0, EPI_POOL = 1 };
