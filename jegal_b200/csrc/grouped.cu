@@ -279,7 +279,10 @@ grouped_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams p) 
   if (warp < 4) {
   if (warp == 0) {
     // (Two producer threads -- frame boxes from warp 0, word boxes from warp 3, barrier count 2 -- were measured twice,
-    // before and after the epilogue / norm warps stopped being the limit: 0.33 vs 0.31 ms on config 3 both times.)
+    // before and after the epilogue / norm warps stopped being the limit: 0.33 vs 0.31 ms on config 3 both times.
+    // Letting the whole warp walk the loop with lane 0 issuing, so that the bookkeeping could live in uniform registers,
+    // does not help either: ptxas does not treat the LDG-derived operands as uniform and wraps every TMA in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY loop -- more instructions per stage, not fewer.)
     if (elect_one()) {
       const uint64_t pol = policy_evict_first();  // every operand byte is used once
       // stage n uses barrier slot n % kGStages; `inflight` = ring bytes of stages not yet released.
